@@ -1,0 +1,158 @@
+"""Freeze golden vectors from the UNMODIFIED reference functions.  TEST INFRASTRUCTURE.
+
+Run in the authoring container (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+Writes tests/golden/*.npz.  The reference functions are executed through
+``oracle.ref_extract`` (AST extraction, NumPy shim); inputs are small seeded synthetic
+arrays so the fixtures stay a few hundred KB.  The GPU box has no /root/reference: tests
+there only read these files.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_extract  # noqa: E402
+from superpixel_align_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _blobs(rs, n, d, k, spread=6.0):
+    cent = rs.standard_normal((k, d)) * spread
+    lab = rs.randint(0, k, n)
+    return cent[lab] + rs.standard_normal((n, d))
+
+
+def gen_kmeans():
+    """Reference kmeans() (batch_spalign_kmeans.py:136-183) on seeded inputs."""
+    ref = ref_extract.load('batch_spalign_kmeans.py', seed=1111)
+    cases = {}
+    rs = np.random.RandomState(7)
+    specs = [  # name, N, D, K
+        ('k4', 240, 10, 4), ('k2', 150, 6, 2), ('k8', 400, 12, 8), ('k3_pos', 300, 18, 3),
+    ]
+    for name, n, d, k in specs:
+        X = _blobs(rs, n, d, k)
+        if name.endswith('pos'):  # last two columns in pixel units like the spalign path
+            X[:, -2] = rs.uniform(0, 1023, n)
+            X[:, -1] = rs.uniform(0, 2047, n)
+        X = X.astype(np.float32).astype(np.float64)  # fp32-representable, as the CUDA path stores it
+        w = rs.uniform(0.0, 1.0, n)
+        state = np.random.get_state()
+        assign = ref.kmeans(k, X, w)
+        after = np.random.get_state()
+        # recover the init the reference drew, by replaying the stream
+        np.random.set_state(state)
+        from oracle import spalign_oracle as so
+        init = so.kmeans_init(k, w)
+        np.random.set_state(after)
+        cases[name] = dict(X=X.astype(np.float32), w=w, k=k, init=init.astype(np.int32),
+                           assign=np.asarray(assign).astype(np.int32))
+    # NaN centre: more clusters than low-prior rows -> empty init clusters
+    X = _blobs(rs, 6, 4, 2).astype(np.float32).astype(np.float64)
+    w = np.array([0.9, 0.1, 0.8, 0.2, 0.7, 0.3])
+    state = np.random.get_state()
+    with np.errstate(all='ignore'):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            assign = ref.kmeans(8, X, w)
+    np.random.set_state(state)
+    from oracle import spalign_oracle as so
+    init = so.kmeans_init(8, w)
+    cases['nan_center'] = dict(X=X.astype(np.float32), w=w, k=8, init=init.astype(np.int32),
+                               assign=np.asarray(assign).astype(np.int32))
+    flat = {}
+    for name, c in cases.items():
+        for key, v in c.items():
+            flat['%s__%s' % (name, key)] = v
+    np.savez_compressed(os.path.join(OUT, 'kmeans_ref.npz'), **flat)
+    print('kmeans_ref.npz:', {n: int(c['assign'].max()) for n, c in cases.items()})
+
+
+def gen_prior():
+    """Reference create_prior() superpixel form (batch_spalign_kmeans.py:111-129) and cell
+    form (direct_clustering.py:188-201)."""
+    ref = ref_extract.load('batch_spalign_kmeans.py')
+    refd = ref_extract.load('direct_clustering.py')
+    lab = synth.voronoi_labels(64, 128, 4, 8, image_index=0)
+    lab2 = synth.voronoi_labels(56, 56, 5, 5, image_index=3)
+    out = dict(
+        lab_a=lab, w_a=ref.create_prior(lab, 0.75, 0.5, 0.1, 0.1),
+        lab_b=lab2, w_b=ref.create_prior(lab2, 0.6, 0.4, 0.2, 0.15),
+        cell_28=refd.create_prior(28, 28, 0.75, 0.5, 0.1, 0.1),
+        cell_16x32=refd.create_prior(16, 32, 0.75, 0.5, 0.1, 0.1),
+    )
+    np.savez_compressed(os.path.join(OUT, 'prior_ref.npz'), **out)
+    print('prior_ref.npz:', out['w_a'].shape, out['w_b'].shape)
+
+
+def gen_weighted_kmeans():
+    """Reference weighted_kmeans() (k-means + paint-back, :186-207) on a 2-image batch, and
+    the reference anchor-sampled superpixel_align (:210-276) for the centroid columns."""
+    ref = ref_extract.load('batch_spalign_kmeans.py', seed=1111)
+    H, W, fh, fw, C = 32, 64, 4, 8, 6
+    labs = np.stack([synth.voronoi_labels(H, W, 3, 5, image_index=i, dtype=np.int64)
+                     for i in range(2)])
+    feats = [synth.smooth_features(C, fh, fw, seed=10 + i, radius=1) for i in range(2)]
+    imgs = np.zeros((2, 3, H, W), dtype=np.float32)
+    sp_feats, n_per = [], []
+    for i in range(2):
+        f = ref.superpixel_align(imgs[i], feats[i], labs[i], 10, 4, True)
+        sp_feats.append(f)
+        n_per.append(len(np.unique(labs[i])))
+    sp_feats = np.concatenate(sp_feats)
+    w = np.concatenate([ref.create_prior(l, 0.75, 0.5, 0.1, 0.1) for l in labs])
+    state = np.random.get_state()
+    cres, road = ref.weighted_kmeans(labs, sp_feats, w, 3, n_per)
+    np.random.set_state(state)
+    from oracle import spalign_oracle as so
+    init = so.kmeans_init(3, w)
+    np.savez_compressed(
+        os.path.join(OUT, 'weighted_kmeans_ref.npz'), labs=labs, feats=np.stack(feats),
+        anchor_features=sp_feats, weights=w, n_per=np.array(n_per), k=3,
+        init=init.astype(np.int32), cluster_map=cres, road=road)
+    print('weighted_kmeans_ref.npz:', sp_feats.shape, cres.shape, int(road.sum()))
+
+
+def gen_overlap():
+    """No reference source exists for the count matrix (parity unpinned).  Freeze the
+    oracle's CSR for three small maps as a regression fixture, after cross-checking it
+    against the reference-style mask loop."""
+    from oracle import spalign_oracle as so
+    out = {}
+    for name, lab, fh, fw in [
+        ('vor', synth.voronoi_labels(64, 128, 4, 8, image_index=1), 8, 16),
+        ('ragged', synth.voronoi_labels(50, 70, 3, 4, image_index=2), 7, 9),
+        ('noise', synth.noise_labels(24, 40, 17, seed=5), 3, 5),
+    ]:
+        ip, ix, ct = so.overlap_csr(lab, fh, fw)
+        H, W = lab.shape
+        cell = so.cell_of_pixel(H, fh)[:, None] * fw + so.cell_of_pixel(W, fw)[None, :]
+        for s in range(len(ip) - 1):  # mask-loop cross-check
+            m = lab == s
+            cols, cnt = np.unique(cell[m], return_counts=True)
+            assert np.array_equal(cols, ix[ip[s]:ip[s + 1]])
+            assert np.array_equal(cnt, ct[ip[s]:ip[s + 1]])
+        out.update({name + '__label': lab, name + '__fh': fh, name + '__fw': fw,
+                    name + '__indptr': ip, name + '__indices': ix, name + '__counts': ct})
+    np.savez_compressed(os.path.join(OUT, 'overlap_oracle.npz'), **out)
+    print('overlap_oracle.npz ok')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    random.seed(1111)
+    gen_kmeans()
+    gen_prior()
+    gen_weighted_kmeans()
+    gen_overlap()

@@ -1,0 +1,387 @@
+"""CPU oracle for the superpixel-align hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy restatement of the reference algorithm (pfnet-research/
+superpixel-align).  It is the *checker*: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The
+product (``superpixel_align_b200``) never imports anything from ``oracle/`` and has
+no CPU fallback.
+
+Pinning status (see DESIGN.md "Oracle"):
+  * ``kmeans``, ``kmeans_init``, ``weighted_average``, ``create_prior``,
+    ``create_prior_map``, ``weighted_kmeans_paint`` are pinned against the reference's
+    own functions executed unmodified (``oracle/ref_extract.py`` AST-extracts them from
+    ``/root/reference`` in the authoring container; ``oracle/gen_golden.py`` froze their
+    outputs into ``tests/golden/*.npz``).
+  * ``overlap_csr`` / ``pool_count`` have NO in-tree reference source
+    (``notebooks/Efficient_Superpixel_Align.ipynb`` is listed in
+    ``.MISSING_LARGE_BLOBS``): **parity unpinned by the reference** for these two; the
+    contract is the one fixed in SURVEY.md section 8 (a1, a2).  They are cross-checked
+    against the reference's mask-based loops (``superpixel_overlaps.py:359-369`` and
+    ``scipy.ndimage.center_of_mass`` as used at ``batch_spalign_kmeans.py:229``).
+  * ``confusion`` / ``road_iou`` restate chainercv 0.7/0.8 semantics from memory
+    (chainercv is not in the tree): parity unpinned.
+
+All line numbers refer to files under ``/root/reference``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# a1. overlap (count) matrix
+# --------------------------------------------------------------------------------------
+
+
+def cell_of_pixel(n_pix: int, n_cell: int) -> np.ndarray:
+    """Nearest-neighbour pixel -> cell map, ``min(floor(p * n_cell / n_pix), n_cell-1)``.
+
+    Identical to cv2.resize(..., INTER_NEAREST) source-index selection, which is how the
+    reference upsamples a cell mask to pixel resolution (superpixel_overlaps.py:360-362).
+    """
+    p = np.arange(n_pix, dtype=np.int64)
+    return np.minimum((p * n_cell) // n_pix, n_cell - 1).astype(np.int64)
+
+
+def overlap_csr(label: np.ndarray, fh: int, fw: int, n_sp: int | None = None):
+    """CSR overlap matrix M[s, c] = #pixels with label s that fall in feature cell c.
+
+    Contract: rows = labels 0..S-1, columns ascending cell id
+    (cell = cy * fw + cx), int32 counts.  Returns (indptr[S+1], indices[nnz], counts[nnz])
+    as int32 arrays.
+    """
+    label = np.asarray(label)
+    H, W = label.shape
+    if n_sp is None:
+        n_sp = int(label.max()) + 1
+    cy = cell_of_pixel(H, fh)
+    cx = cell_of_pixel(W, fw)
+    cell = cy[:, None] * fw + cx[None, :]
+    nc = fh * fw
+    key = label.astype(np.int64).ravel() * nc + cell.ravel()
+    uk, cnt = np.unique(key, return_counts=True)
+    rows = uk // nc
+    cols = uk % nc
+    indptr = np.zeros(n_sp + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr.astype(np.int32), cols.astype(np.int32), cnt.astype(np.int32)
+
+
+def superpixel_stats(label: np.ndarray, n_sp: int | None = None):
+    """Per-superpixel pixel count, sum of y and sum of x (exact integers).
+
+    centroid = (sum_y/area, sum_x/area) equals scipy.ndimage.center_of_mass(mask) used
+    at batch_spalign_kmeans.py:229.
+    """
+    label = np.asarray(label)
+    H, W = label.shape
+    if n_sp is None:
+        n_sp = int(label.max()) + 1
+    flat = label.ravel().astype(np.int64)
+    area = np.bincount(flat, minlength=n_sp).astype(np.int64)
+    yy = np.repeat(np.arange(H, dtype=np.int64), W)
+    xx = np.tile(np.arange(W, dtype=np.int64), H)
+    # bincount with integer-valued float64 weights is exact below 2**53
+    sum_y = np.bincount(flat, weights=yy, minlength=n_sp).astype(np.int64)
+    sum_x = np.bincount(flat, weights=xx, minlength=n_sp).astype(np.int64)
+    return area, sum_y, sum_x
+
+
+# --------------------------------------------------------------------------------------
+# a3. prior
+# --------------------------------------------------------------------------------------
+
+
+def create_prior_map(h, w, y_rel_pos=0.75, x_rel_pos=0.5, y_rel_sigma=0.1, x_rel_sigma=0.2):
+    """Gaussian road prior on an h x w grid (direct_clustering.py:188-201 and the
+    pixel-level map inside batch_spalign_kmeans.py:111-122).  Note ``(2*sigma)**2``."""
+    xcoord, ycoord = np.meshgrid(np.arange(w), np.arange(h))
+    ymean, xmean = int(h * y_rel_pos), int(w * x_rel_pos)
+    y_sigma = h * y_rel_sigma
+    x_sigma = w * x_rel_sigma
+    return np.exp(-((ycoord - ymean) ** 2 / (2 * y_sigma) ** 2
+                    + (xcoord - xmean) ** 2 / (2 * x_sigma) ** 2))
+
+
+def prior_axes(h, w, y_rel_pos=0.75, x_rel_pos=0.5, y_rel_sigma=0.1, x_rel_sigma=0.2):
+    """Separable factors gy[h], gx[w] with create_prior_map == outer(gy, gx) up to 1 ulp."""
+    ymean, xmean = int(h * y_rel_pos), int(w * x_rel_pos)
+    y_sigma = h * y_rel_sigma
+    x_sigma = w * x_rel_sigma
+    gy = np.exp(-((np.arange(h) - ymean) ** 2 / (2 * y_sigma) ** 2))
+    gx = np.exp(-((np.arange(w) - xmean) ** 2 / (2 * x_sigma) ** 2))
+    return gy, gx
+
+
+def create_prior(superpixels, y_rel_pos=0.75, x_rel_pos=0.5, y_rel_sigma=0.1,
+                 x_rel_sigma=0.2):
+    """Mean prior weight per superpixel, sorted-label order
+    (batch_spalign_kmeans.py:111-129).  float64 [S]."""
+    superpixels = np.asarray(superpixels)
+    h, w = superpixels.shape
+    weights = create_prior_map(h, w, y_rel_pos, x_rel_pos, y_rel_sigma, x_rel_sigma)
+    ids, inv = np.unique(superpixels, return_inverse=True)
+    inv = inv.ravel()
+    s = np.bincount(inv, weights=weights.ravel(), minlength=len(ids))
+    n = np.bincount(inv, minlength=len(ids))
+    return s / n
+
+
+# --------------------------------------------------------------------------------------
+# a2. count pooling
+# --------------------------------------------------------------------------------------
+
+
+def pool_count(indptr, indices, counts, feat_cellmajor, area=None, sum_y=None, sum_x=None,
+               append_pos=True):
+    """feat[s, :C] = sum_c M[s,c] * F[c,:] / area[s]; optional (sum_y/area, sum_x/area).
+
+    ``feat_cellmajor`` is [Nc, C] (= feature_map[C, fh, fw].reshape(C, -1).T).  float64 out.
+    Contract fixed in SURVEY 8 a2 (count pooling = mean over all member pixels of the
+    nearest-upsampled feature map); centroid columns follow batch_spalign_kmeans.py:229,270.
+    """
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    counts = np.asarray(counts, dtype=np.float64)
+    F = np.asarray(feat_cellmajor, dtype=np.float64)
+    S = len(indptr) - 1
+    C = F.shape[1]
+    out = np.zeros((S, C + (2 if append_pos else 0)), dtype=np.float64)
+    rowsum = np.zeros(S, dtype=np.float64)
+    for s in range(S):
+        a, b = indptr[s], indptr[s + 1]
+        if b > a:
+            out[s, :C] = counts[a:b] @ F[indices[a:b]]
+            rowsum[s] = counts[a:b].sum()
+    if area is None:
+        area = rowsum
+    area = np.asarray(area, dtype=np.float64)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        out[:, :C] /= area[:, None]
+        if append_pos:
+            out[:, C] = np.asarray(sum_y, dtype=np.float64) / area
+            out[:, C + 1] = np.asarray(sum_x, dtype=np.float64) / area
+    return out
+
+
+def pool_dense_nearest(label, feature_map, append_pos=True):
+    """Independent formulation of count pooling: nearest-upsample the [C, fh, fw] map to
+    H x W and take the mean over each superpixel's pixels.  O(H*W*C) -- small inputs only.
+    Used to cross-check ``overlap_csr`` + ``pool_count``."""
+    label = np.asarray(label)
+    H, W = label.shape
+    C, fh, fw = feature_map.shape
+    cy = cell_of_pixel(H, fh)
+    cx = cell_of_pixel(W, fw)
+    up = np.asarray(feature_map, dtype=np.float64)[:, cy][:, :, cx]  # [C, H, W]
+    S = int(label.max()) + 1
+    out = np.zeros((S, C + (2 if append_pos else 0)))
+    for s in range(S):
+        m = label == s
+        out[s, :C] = up[:, m].mean(axis=1)
+        if append_pos:
+            ys, xs = np.nonzero(m)
+            out[s, C] = ys.mean()
+            out[s, C + 1] = xs.mean()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a4, a5. prior-weighted k-means
+# --------------------------------------------------------------------------------------
+
+
+def weighted_average(a, b, axis=0):
+    """batch_spalign_kmeans.py:132-133."""
+    return (a * b[:, None]).sum(axis=axis) / b.sum(axis=axis)
+
+
+def kmeans_init(k, weights, rng=None):
+    """Initial assignment (batch_spalign_kmeans.py:141-149).
+
+    Rows whose prior weight is above the upper median go to cluster 0; the rest get
+    1..k-1 round-robin, shuffled with the (legacy, process-global) NumPy stream.
+    Returns float64 [N] exactly like the reference's ``assign`` array.
+    """
+    rng = np.random if rng is None else rng
+    weights = np.asarray(weights)
+    n = weights.shape[0]
+    assign = np.zeros((n,))
+    thr = float(np.sort(weights)[n // 2])
+    cond = weights <= thr
+    idx = np.arange(int(cond.sum())) % (k - 1) + 1
+    rng.shuffle(idx)
+    assign[cond] = idx
+    return assign
+
+
+def kmeans(k, X, weights, n_iter=1000, init_assign=None, rng=None, return_info=False,
+           verbose=True):
+    """Prior-weighted k-means, restating batch_spalign_kmeans.py:136-183.
+
+    ``init_assign`` (optional) replaces the seeded init so the CUDA path and the oracle
+    start identically.  status: 0 = assignments stopped changing, 1 = stopped on an empty
+    cluster, 2 = iteration cap.
+    """
+    X = np.asarray(X)
+    weights = np.asarray(weights)
+    weights_other = 1 - weights
+    if init_assign is None:
+        assign = kmeans_init(k, weights, rng)
+    else:
+        assign = np.asarray(init_assign)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            centers = np.stack([X[assign == i].mean(axis=0) for i in np.arange(k)])
+        status, iters = 2, 0
+        for _ in range(n_iter):
+            iters += 1
+            distances = np.linalg.norm(X[:, None, :] - centers[None, :, :], axis=2)
+            new_assign = np.argmin(distances, axis=1).astype(np.int32)
+            if np.all(new_assign == assign):
+                status = 0
+                break
+            assign = new_assign
+            mask = assign == 0
+            centers[0] = weighted_average(X[mask], weights[mask], axis=0)
+            for j in range(1, k):
+                mask = assign == j
+                centers[j] = weighted_average(X[mask], weights_other[mask], axis=0)
+            done = False
+            for j in range(k):
+                if (assign == j).sum() == 0:
+                    if verbose:
+                        print(('Terminate KMeans iteration due to {}-th cluster is '
+                               'empty').format(j))
+                    done = True
+                    break
+            if done:
+                status = 1
+                break
+    if return_info:
+        return assign, dict(iters=iters, status=status, centers=centers)
+    return assign
+
+
+# --------------------------------------------------------------------------------------
+# a6. paint-back
+# --------------------------------------------------------------------------------------
+
+
+def weighted_kmeans_paint(superpixels, result, n_superpixels_per_image):
+    """Paint cluster ids back to pixels (batch_spalign_kmeans.py:191-207), as a gather.
+
+    The reference uses the enumerate index as the label (labels assumed 0..n_i-1) and
+    leaves pixels whose label is >= n_i at 0 (zeros_like)."""
+    superpixels = np.asarray(superpixels)
+    out = np.zeros_like(superpixels)
+    i = 0
+    for img_idx, n_sp in enumerate(n_superpixels_per_image):
+        table = np.asarray(result[i:i + n_sp]).astype(superpixels.dtype)
+        lab = superpixels[img_idx]
+        ok = (lab >= 0) & (lab < n_sp)
+        out[img_idx][ok] = table[lab[ok]]
+        i += n_sp
+    return out, out == 0
+
+
+# --------------------------------------------------------------------------------------
+# a7. overlap refine (superpixel_overlaps.py:359-369)
+# --------------------------------------------------------------------------------------
+
+
+def refine_overlaps_csr(indptr, indices, counts, road_cell, thr):
+    """keep[s] = road_px > 0 and (sum_c M[s,c]*road[c]) / road_px > thr, with road_px the
+    number of road pixels of the nearest-upsampled cell mask (= sum_s overlap[s])."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    road = np.asarray(road_cell).ravel().astype(np.int64)
+    contrib = np.asarray(counts, dtype=np.int64) * road[np.asarray(indices, dtype=np.int64)]
+    csum = np.concatenate([[0], np.cumsum(contrib)])
+    overlap = csum[indptr[1:]] - csum[indptr[:-1]]
+    road_px = int(overlap.sum())
+    keep = np.zeros(len(overlap), dtype=bool)
+    if road_px > 0:
+        keep = (overlap.astype(np.float64) / float(road_px)) > thr
+    return overlap, road_px, keep
+
+
+def refine_overlaps_masks(superpixel, road_mask, thr):
+    """Literal restatement of the reference loop on pixel masks (small inputs only)."""
+    superpixel = np.asarray(superpixel)
+    road_mask = np.asarray(road_mask).astype(np.uint8)
+    refined = np.zeros_like(road_mask)
+    n_road = float(np.sum(road_mask))
+    for idx in np.unique(superpixel):
+        sp_mask = superpixel == idx
+        overlap = float(np.sum(np.asarray(sp_mask, dtype=np.int32) * road_mask))
+        if n_road > 0 and (overlap / float(n_road)) > thr:
+            refined[sp_mask] = 1
+    return refined
+
+
+def upsample_nearest(mask_cells, H, W):
+    fh, fw = mask_cells.shape
+    return np.asarray(mask_cells)[cell_of_pixel(H, fh)][:, cell_of_pixel(W, fw)]
+
+
+# --------------------------------------------------------------------------------------
+# a8. direct feature matrix (direct_clustering.py:297-303)
+# --------------------------------------------------------------------------------------
+
+
+def direct_features(feature_maps):
+    """[n, C, h, w] -> float64 [n*h*w, C+2]; last two columns are (x, y) CELL indices."""
+    feature_maps = np.asarray(feature_maps)
+    n, c, h, w = feature_maps.shape
+    xy = np.stack(np.meshgrid(np.arange(w), np.arange(h))).reshape(2, -1)[None].repeat(n, axis=0)
+    xy = xy.transpose(0, 2, 1).reshape(-1, 2).astype(np.int32)
+    fm = feature_maps.transpose(0, 2, 3, 1).reshape(n * h * w, c)
+    return np.concatenate([fm, xy], axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# evaluation (chainercv semantics restated; batch_spalign_kmeans.py:398-405)
+# --------------------------------------------------------------------------------------
+
+
+def confusion(pred, gt, n_class=2):
+    pred = np.asarray(pred).ravel().astype(np.int64)
+    gt = np.asarray(gt).ravel().astype(np.int64)
+    m = gt >= 0
+    return np.bincount(n_class * gt[m] + pred[m], minlength=n_class ** 2).reshape(n_class, n_class)
+
+
+def road_iou(pred_road, gt):
+    """gt: -1 void, 1 road, 0 other.  Returns (iou_road, precision, recall, TP, FP, FN)."""
+    conf = confusion(pred_road, gt, 2)
+    tp, fp, fn = conf[1, 1], conf[0, 1], conf[1, 0]
+    with np.errstate(invalid='ignore', divide='ignore'):
+        iou = tp / float(tp + fp + fn)
+        prec = tp / float(tp + fp)
+        rec = tp / float(tp + fn)
+    return iou, prec, rec, int(tp), int(fp), int(fn)
+
+
+# --------------------------------------------------------------------------------------
+# whole path on CPU (cpu_baseline "port")
+# --------------------------------------------------------------------------------------
+
+
+def spalign_image_cpu(label, feat_cellmajor, fh, fw, k=4, prior=(0.75, 0.5, 0.1, 0.1),
+                      append_pos=True, init_assign=None, rng=None):
+    """One image through the count-matrix path on the CPU: overlap CSR -> pooling ->
+    prior -> weighted k-means -> paint.  Returns dict of all intermediates."""
+    label = np.asarray(label)
+    n_sp = int(label.max()) + 1
+    indptr, indices, counts = overlap_csr(label, fh, fw, n_sp)
+    area, sy, sx = superpixel_stats(label, n_sp)
+    feat = pool_count(indptr, indices, counts, feat_cellmajor, area, sy, sx, append_pos)
+    w = create_prior(label, *prior)
+    assign, info = kmeans(k, feat, w, init_assign=init_assign, rng=rng, return_info=True,
+                          verbose=False)
+    cmap, road = weighted_kmeans_paint(label[None], assign, [n_sp])
+    return dict(indptr=indptr, indices=indices, counts=counts, area=area, sum_y=sy, sum_x=sx,
+                features=feat, weights=w, assign=assign, info=info, cluster_map=cmap[0],
+                road_mask=road[0])

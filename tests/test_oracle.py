@@ -1,0 +1,154 @@
+"""CPU tests: pin the oracle (oracle/spalign_oracle.py) against golden vectors frozen from
+the unmodified reference functions (oracle/gen_golden.py), and, where /root/reference is
+present, against the reference functions executed live."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_extract
+from oracle import spalign_oracle as so
+from superpixel_align_b200 import synth
+
+
+def _cases(npz):
+    names = sorted({k.split('__')[0] for k in npz.files})
+    return {n: {k.split('__')[1]: npz[k] for k in npz.files if k.startswith(n + '__')}
+            for n in names}
+
+
+def test_kmeans_matches_reference_golden(golden_dir):
+    cases = _cases(np.load(os.path.join(golden_dir, 'kmeans_ref.npz')))
+    assert set(cases) == {'k4', 'k2', 'k8', 'k3_pos', 'nan_center'}
+    for name, c in cases.items():
+        got = so.kmeans(int(c['k']), c['X'].astype(np.float64), c['w'],
+                        init_assign=c['init'].astype(np.float64), verbose=False)
+        assert np.array_equal(np.asarray(got).astype(np.int32), c['assign']), name
+
+
+def test_kmeans_nan_center_known_answer(golden_dir):
+    c = _cases(np.load(os.path.join(golden_dir, 'kmeans_ref.npz')))['nan_center']
+    # k=8 with 6 rows: init clusters 5..7 are empty -> NaN centres -> numpy argmin returns
+    # the first NaN column for every row
+    assert np.all(c['assign'] == 5)
+
+
+def test_prior_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'prior_ref.npz'))
+    np.testing.assert_allclose(so.create_prior(g['lab_a'], 0.75, 0.5, 0.1, 0.1), g['w_a'],
+                               rtol=1e-13, atol=0)
+    np.testing.assert_allclose(so.create_prior(g['lab_b'], 0.6, 0.4, 0.2, 0.15), g['w_b'],
+                               rtol=1e-13, atol=0)
+    assert np.array_equal(so.create_prior_map(28, 28, 0.75, 0.5, 0.1, 0.1), g['cell_28'])
+    assert np.array_equal(so.create_prior_map(16, 32, 0.75, 0.5, 0.1, 0.1), g['cell_16x32'])
+    gy, gx = so.prior_axes(16, 32, 0.75, 0.5, 0.1, 0.1)
+    np.testing.assert_allclose(np.outer(gy, gx), g['cell_16x32'], rtol=4e-15, atol=1e-300)  # separable form: few-ulp
+
+
+def test_paint_and_centroids_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'weighted_kmeans_ref.npz'))
+    labs, n_per = g['labs'], list(g['n_per'])
+    assign = so.kmeans(int(g['k']), g['anchor_features'], g['weights'],
+                       init_assign=g['init'].astype(np.float64), verbose=False)
+    cmap, road = so.weighted_kmeans_paint(labs, assign, n_per)
+    assert cmap.dtype == labs.dtype
+    assert np.array_equal(cmap, g['cluster_map'])
+    assert np.array_equal(road, g['road'])
+    # centroid columns of the reference's anchor path == exact integer sums / area
+    off = 0
+    for i, n in enumerate(n_per):
+        area, sy, sx = so.superpixel_stats(labs[i], n)
+        # (1 ulp slack: the reference averages 10 identical centroid copies, :270-274)
+        np.testing.assert_allclose(g['anchor_features'][off:off + n, -2], sy / area, rtol=1e-15)
+        np.testing.assert_allclose(g['anchor_features'][off:off + n, -1], sx / area, rtol=1e-15)
+        off += n
+
+
+def test_overlap_regression_golden(golden_dir):
+    cases = _cases(np.load(os.path.join(golden_dir, 'overlap_oracle.npz')))
+    for name, c in cases.items():
+        ip, ix, ct = so.overlap_csr(c['label'], int(c['fh']), int(c['fw']))
+        assert np.array_equal(ip, c['indptr']) and np.array_equal(ix, c['indices']) \
+            and np.array_equal(ct, c['counts']), name
+        assert ct.sum() == c['label'].size
+        for s in range(len(ip) - 1):
+            assert np.all(np.diff(ix[ip[s]:ip[s + 1]]) > 0)
+
+
+@pytest.mark.parametrize('H,W,fh,fw,gy,gx', [(64, 128, 8, 16, 4, 8), (50, 70, 7, 9, 3, 4),
+                                             (224, 224, 28, 28, 7, 7)])
+def test_pool_count_equals_dense_nearest(H, W, fh, fw, gy, gx):
+    lab = synth.voronoi_labels(H, W, gy, gx, image_index=4)
+    F = synth.smooth_features(5, fh, fw, seed=3, radius=1)
+    ip, ix, ct = so.overlap_csr(lab, fh, fw)
+    area, sy, sx = so.superpixel_stats(lab)
+    assert np.array_equal(np.diff(np.concatenate([[0], np.cumsum(ct)])[ip]), area)
+    got = so.pool_count(ip, ix, ct, F.reshape(5, -1).T, area, sy, sx, True)
+    want = so.pool_dense_nearest(lab, F, True)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_cell_map_matches_cv2_nearest():
+    cv = pytest.importorskip('cv2')
+    for (fh, fw, H, W) in [(128, 256, 1024, 2048), (28, 28, 224, 224), (30, 60, 1024, 2048),
+                           (7, 9, 50, 70)]:
+        ids = np.arange(fh * fw, dtype=np.float32).reshape(fh, fw)
+        up = cv.resize(ids, (W, H), interpolation=cv.INTER_NEAREST).astype(np.int64)
+        mine = so.cell_of_pixel(H, fh)[:, None] * fw + so.cell_of_pixel(W, fw)[None, :]
+        assert np.array_equal(up, mine)
+
+
+def test_refine_csr_equals_mask_loop():
+    lab = synth.voronoi_labels(64, 96, 4, 6, image_index=9)
+    fh, fw = 8, 12
+    rs = np.random.RandomState(0)
+    road_cell = rs.rand(fh, fw) < 0.3
+    ip, ix, ct = so.overlap_csr(lab, fh, fw)
+    for thr in (0.01, 0.05, 0.2):
+        ov, road_px, keep = so.refine_overlaps_csr(ip, ix, ct, road_cell, thr)
+        want = so.refine_overlaps_masks(lab, so.upsample_nearest(road_cell, 64, 96), thr)
+        assert road_px == so.upsample_nearest(road_cell, 64, 96).sum()
+        assert np.array_equal(keep[lab].astype(np.uint8), want)
+
+
+def test_direct_features_layout():
+    F = np.arange(2 * 3 * 4 * 5, dtype=np.float32).reshape(2, 3, 4, 5)
+    X = so.direct_features(F)
+    assert X.shape == (40, 5) and X.dtype == np.float64
+    assert np.array_equal(X[7, :3], F[0, :, 1, 2]) and tuple(X[7, 3:]) == (2.0, 1.0)  # (x, y)
+    assert np.array_equal(X[20 + 19, :3], F[1, :, 3, 4]) and tuple(X[39, 3:]) == (4.0, 3.0)
+
+
+def test_road_iou():
+    gt = np.array([[1, 1, 0, -1], [0, 1, 0, 0]])
+    pred = np.array([[1, 0, 1, 1], [0, 1, 0, 0]])
+    iou, prec, rec, tp, fp, fn = so.road_iou(pred, gt)
+    assert (tp, fp, fn) == (2, 1, 1) and iou == 0.5
+
+
+# ---- live checks against the reference source (authoring container only) -------------
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('script', ['batch_spalign_kmeans.py', 'direct_clustering.py',
+                                    'superpixel_overlaps.py'])
+def test_kmeans_live_reference_same_stream(script):
+    ref = ref_extract.load(script, seed=1111)
+    rs = np.random.RandomState(3)
+    X = np.concatenate([rs.standard_normal((90, 7)) + 5 * rs.standard_normal((1, 7))
+                        for _ in range(4)])
+    w = rs.uniform(0, 1, len(X))
+    for k in (2, 4, 5):
+        np.random.seed(1111)
+        want = ref.kmeans(k, X, w)
+        np.random.seed(1111)
+        got = so.kmeans(k, X, w, verbose=False)
+        assert np.array_equal(np.asarray(want), np.asarray(got))
+
+
+@pytest.mark.needs_reference
+def test_create_prior_live_reference():
+    ref = ref_extract.load('batch_spalign_kmeans.py')
+    lab = synth.blob_labels(40, 60, 12, seed=1)
+    np.testing.assert_allclose(so.create_prior(lab, 0.75, 0.5, 0.1, 0.1),
+                               ref.create_prior(lab, 0.75, 0.5, 0.1, 0.1), rtol=1e-13)
