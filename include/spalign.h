@@ -1,0 +1,202 @@
+/*
+ * spalign.h -- C ABI of libspalign_b200.so: the B200 (sm_100a) hot path of
+ * pfnet-research/superpixel-align.
+ *
+ * The reference has no FFI: its seam is a set of module-level Python functions
+ * (batch_spalign_kmeans.py:316-358, direct_clustering.py:204-208; imported by name at
+ * utils/apply_spalign_kmeans.py:17-21).  The Python drop-ins in superpixel_align_b200/
+ * keep those names and array contracts and call the entry points below through ctypes.
+ * Each entry point cites the reference code it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless marked "host".
+ *   - The library allocates nothing persistent, never synchronises the device and is
+ *     thread-safe per stream.  All work is enqueued on `stream` (a cudaStream_t).
+ *   - Return value: 0 = enqueued OK, otherwise a spalign_status; spalign_last_error()
+ *     gives a thread-local message.  Data-dependent conditions (label out of range, CSR
+ *     capacity overflow, k-means stop reason) are reported in device-side words that the
+ *     caller reads when it next synchronises.
+ *   - Images are row-major [n_img, H, W]; feature cells are cell = cy * fw + cx with
+ *     cy = min(y*fh/H, fh-1), cx = min(x*fw/W, fw-1)  (== cv2 INTER_NEAREST, the
+ *     upsampling used at superpixel_overlaps.py:360-362).
+ *   - "Rows" are superpixels of a batch, numbered sp_off[img] + label.
+ */
+#ifndef SPALIGN_H_
+#define SPALIGN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPALIGN_ABI_VERSION 1
+
+typedef void* spalign_stream_t; /* cudaStream_t */
+
+enum spalign_status {
+  SPALIGN_OK = 0,
+  SPALIGN_E_INVALID = 1,     /* bad argument (shape, alignment, NULL) */
+  SPALIGN_E_CUDA = 2,        /* CUDA runtime error while enqueueing */
+  SPALIGN_E_WORKSPACE = 3,   /* workspace too small */
+  SPALIGN_E_UNSUPPORTED = 4  /* valid but not implemented (e.g. K > 8) */
+};
+
+/* label / output element types */
+#define SPALIGN_I32 0
+#define SPALIGN_I64 1
+#define SPALIGN_U8 2
+/* k-means row element types */
+#define SPALIGN_F32 0
+#define SPALIGN_F64 1
+
+/* bits of the device-side `flags` word written by spalign_overlap_csr */
+#define SPALIGN_F_LABEL_RANGE 1  /* a pixel label was < 0 or >= n_sp of its image */
+#define SPALIGN_F_NNZ_OVERFLOW 2 /* more (superpixel, cell) pairs than nnz_cap */
+#define SPALIGN_F_EMPTY_ROW 4    /* a superpixel id owns no pixel (ids not contiguous) */
+
+/* k-means stop reasons (status words) */
+#define SPALIGN_KM_RUNNING (-1)
+#define SPALIGN_KM_CONVERGED 0     /* all(new_assign == assign), batch_spalign_kmeans.py:158 */
+#define SPALIGN_KM_EMPTY_CLUSTER 1 /* "Terminate KMeans iteration due to ...", :173-181 */
+#define SPALIGN_KM_ITER_CAP 2      /* n_iter exhausted, :153 */
+
+int spalign_abi_version(void);
+const char* spalign_last_error(void);
+
+/* ---- K0: per-image maximum label ------------------------------------------------------
+ * Replaces len(np.unique(superpixel)) at batch_spalign_kmeans.py:321 for contiguous ids
+ * (n_superpixels = max + 1).  max_out[n_img] int32, initialised by the call. */
+int spalign_label_max(const void* labels, int label_dtype, int n_img, int H, int W,
+                      int32_t* max_out, spalign_stream_t stream);
+
+/* ---- K1: label map -> CSR overlap (pixel-count) matrix + per-superpixel statistics ----
+ * Replaces the S full-image boolean masks of batch_spalign_kmeans.py:226-233 (membership),
+ * :229 (center_of_mass), create_prior :111-129 (mean prior per superpixel) and the overlap
+ * loop superpixel_overlaps.py:365-369.  The count matrix itself has no in-tree source
+ * (notebooks/Efficient_Superpixel_Align.ipynb is a missing blob); contract: SURVEY 8 a1.
+ *
+ *   labels   [n_img,H,W] int32 or int64 (label_dtype)
+ *   sp_off   [n_img+1] int64 device, row offset of each image; n_rows = sp_off[n_img] (host)
+ *   gy, gx   [H], [W] float64 separable prior factors (NULL -> sum_prior not computed)
+ *   indptr   [n_rows+1] int32, indices/counts [nnz_cap] int32: columns ascending per row
+ *   area     [n_rows] int32; sum_y,sum_x [n_rows] int64 (exact); sum_prior [n_rows] float64
+ *   nnz_flags  int64[4] device: [0] = nnz, [1] = OR of SPALIGN_F_* bits, [2] = largest number of
+ *              pairs any one image produced (lower bound when pathological cells bypass the
+ *              staging buffer), [3] reserved.  Each image may hold nnz_cap / n_img pairs.
+ * Results are bit-reproducible run to run (no floating-point atomics). */
+size_t spalign_overlap_workspace_bytes(int n_img, int H, int W, int fh, int fw,
+                                       int64_t n_rows, int64_t nnz_cap);
+int spalign_overlap_csr(const void* labels, int label_dtype, int n_img, int H, int W, int fh,
+                        int fw, const int64_t* sp_off, int64_t n_rows, const double* gy,
+                        const double* gx, int64_t nnz_cap, int32_t* indptr, int32_t* indices,
+                        int32_t* counts, int32_t* area, int64_t* sum_y, int64_t* sum_x,
+                        double* sum_prior, int64_t* nnz_flags, void* workspace,
+                        size_t ws_bytes, spalign_stream_t stream);
+
+/* ---- K2: superpixel-align pooling (CSR SpMM) ------------------------------------------
+ * Replaces superpixel_align() batch_spalign_kmeans.py:210-276 / batch_superpixel_align
+ * :316-330 under the count-pooling contract:
+ *   out[r, :C] = sum_j counts[j] * feat[img(r), indices[j], :] / area[r]
+ *   out[r, C:C+2] = (sum_y/area, sum_x/area) in image pixels when append_pos
+ *   feat  [n_img, fh*fw, C] float32, CELL-MAJOR (PyTorch channels_last of [n,C,fh,fw])
+ *   out   [n_rows, ld_out] float32, ld_out >= C + 2*append_pos, ld_out % 4 == 0
+ * Summation order is ascending cell id (fixed), accumulation in fp32. */
+int spalign_pool(const float* feat, int n_img, int C, int fh, int fw, const int64_t* sp_off,
+                 int64_t n_rows, int max_rows_per_image, const int32_t* indptr,
+                 const int32_t* indices, const int32_t* counts, const int32_t* area,
+                 const int64_t* sum_y, const int64_t* sum_x, int append_pos, float* out,
+                 int64_t ld_out, spalign_stream_t stream);
+
+/* Layout helper: [n_img, C, ncell] (NCHW, what F.concat yields at batch_spalign_kmeans.py:435)
+ * -> [n_img, ncell, C] cell-major.  direct_clustering.py:302 does the same transpose. */
+int spalign_nchw_to_cellmajor(const float* src, float* dst, int n_img, int C, int ncell,
+                              spalign_stream_t stream);
+
+/* ---- K3: prior-weighted k-means --------------------------------------------------------
+ * Replaces kmeans() batch_spalign_kmeans.py:136-183 (== direct_clustering.py:115-165,
+ * superpixel_overlaps.py:121-171).  Semantics kept: unweighted init means (:150-151),
+ * L2 distance + first-minimum argmin with NumPy NaN rules (:155-157), stop when the
+ * assignment is unchanged (:158), cluster 0 averaged with w and the others with 1-w
+ * (:163-171), stop on an empty cluster after adopting the new assignment (:173-181).
+ * Distances and centroid sums are computed in float64.
+ *
+ *   X        [N, ldx] rows of float32/float64 (x_dtype); row stride ldx elements, rows
+ *            16-byte aligned.  pos_mode 1 appends two virtual columns (x, y) = cell
+ *            indices of row n (direct_clustering.py:297-303): x = (n % pos_period) % pos_w,
+ *            y = (n % pos_period) / pos_w; D counts them.
+ *   w        [N] float64 prior weights
+ *   assign   [N] int32 in/out: initial assignment in, final assignment out
+ *   group_off[G+1] int64 device: G independent problems over contiguous row ranges
+ *   centers  [G, K, D] float64 out (may be NULL for spalign_kmeans_groups)
+ *   iters / status [G] int32 out
+ */
+size_t spalign_kmeans_groups_workspace_bytes(int D, int K, int G);
+/* one persistent CTA per group; the whole iteration loop runs on the device */
+int spalign_kmeans_groups(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                          int64_t pos_period, const double* w, int D, int K, int n_iter,
+                          const int64_t* group_off, int G, int32_t* assign, double* centers,
+                          int32_t* iters, int32_t* status, void* workspace, size_t ws_bytes,
+                          spalign_stream_t stream);
+
+/* multi-CTA building blocks for large groups and for the multi-GPU global clustering:
+ *   chunks [n_chunks,3] int64 device: (group, row_begin, row_end), sorted by group
+ *   group_chunk_off [G+1] int32 device
+ *   partials [n_chunks, K*(D+2)+1] float64: per chunk and cluster k the D sums of omega*x,
+ *            then sum(omega) and the member count ([K][D+2]); last element = #rows changed
+ *   totals   [G, K*(D+2)+1] float64: fixed-order sum over the group's chunks
+ *   mode 0: accumulate init means for the given assignment (omega = 1, no reassignment)
+ *   mode 1: reassign rows against `centers`, count changes, accumulate with prior weights
+ * A multi-GPU caller all-reduces `totals` (NCCL, float64 sum) between reduce and update. */
+int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                         int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
+                         const int64_t* chunks, int n_chunks, const double* centers, int mode,
+                         int32_t* assign, const int32_t* status, double* partials,
+                         spalign_stream_t stream);
+int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
+                          int K, double* totals, spalign_stream_t stream);
+int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,
+                          double* centers, int32_t* iters, int32_t* status,
+                          spalign_stream_t stream);
+
+/* Device-side seeded init for many small groups (batch_spalign_kmeans.py:141-149):
+ * thr = sort(w_g)[N_g/2]; rows with w > thr -> 0; the others take shuffled[g_shuf_off + i]
+ * in row order.  `shuffled` holds, per group, arange(m) % (K-1) + 1 already shuffled by the
+ * host with the NumPy legacy stream for the expected m = N_g/2 + 1; status_m[g] receives
+ * the actual m so the host can detect a tie-induced mismatch (-1: group larger than the
+ * 4096-row shared-memory sort, initialise on the host instead). */
+int spalign_kmeans_init(const double* w, const int64_t* group_off, int G,
+                        const int32_t* shuffled, const int64_t* shuf_off, int32_t* assign,
+                        int32_t* m_out, spalign_stream_t stream);
+
+/* ---- K4: paint-back -------------------------------------------------------------------
+ * Replaces the double loop of weighted_kmeans() batch_spalign_kmeans.py:193-199 and the
+ * `== 0` road mask (:207): cluster_map[p] = table[sp_off[img] + label[p]] (0 when the label
+ * is outside [0, n_sp)), road_mask[p] = (cluster_map[p] == road_value).
+ *   cluster_map: element type out_dtype (SPALIGN_U8 / I32 / I64), may be NULL
+ *   road_mask:   uint8 0/1, may be NULL */
+int spalign_paint(const void* labels, int label_dtype, int n_img, int H, int W,
+                  const int64_t* sp_off, const int32_t* table, void* cluster_map, int out_dtype,
+                  uint8_t* road_mask, int road_value, spalign_stream_t stream);
+
+/* ---- K5: overlap refine ---------------------------------------------------------------
+ * Replaces superpixel_overlaps.py:359-369: overlap[r] = sum_j counts[j]*road_cell[indices[j]],
+ * road_px[img] = sum of overlap over the image's rows, keep[r] = road_px > 0 and
+ * overlap/road_px > thr (float64 compare).  keep is int32 so it can be painted with K4. */
+int spalign_refine(const int64_t* sp_off, int n_img, int64_t n_rows, int ncell,
+                   int max_rows_per_image, const int32_t* indptr, const int32_t* indices, const int32_t* counts,
+                   const uint8_t* road_cell, double thr, int64_t* overlap, int64_t* road_px,
+                   int32_t* keep, spalign_stream_t stream);
+
+/* ---- evaluation -----------------------------------------------------------------------
+ * Replaces chainercv calc_semantic_segmentation_confusion as used at
+ * batch_spalign_kmeans.py:398-402 for 2 classes: conf[img, gt*2+pred] over pixels gt >= 0. */
+int spalign_confusion2(const uint8_t* pred, const int32_t* gt, int n_img, int64_t n_pix,
+                       int64_t* conf, spalign_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPALIGN_H_ */

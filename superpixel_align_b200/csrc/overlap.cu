@@ -1,0 +1,673 @@
+// K0/K1: SLIC label map -> CSR overlap (pixel-count) matrix + per-superpixel statistics.
+//
+// Replaces the S full-image boolean masks of the reference (batch_spalign_kmeans.py:226-233,
+// create_prior :111-129, superpixel_overlaps.py:365-369) with one integer pass over the
+// label map.  Pipeline (all on one stream, no host sync):
+//
+//   init      zero counters / accumulators
+//   emit      one thread per feature cell: distinct labels of the cell -> (row, cell, count,
+//             sum_y, sum_x, prior) pairs, staged in shared memory, flushed with one global
+//             allocation per block; integer atomics for row lengths and centroid sums
+//   scan      row lengths -> indptr (two-level), heavy-row list
+//   scatter   pairs -> their row segment (arbitrary order inside the row)
+//   rowsort   per row: rank-sort by cell id (a warp per row; rows longer than 256 cells go
+//             through a dense scatter/compact path), area and prior summed in column order
+//
+// The only floating-point reduction (prior) is summed in sorted column order with a fixed
+// tree, so the whole result is bit-reproducible.
+#include "common.cuh"
+
+namespace spalign {
+namespace {
+
+constexpr int EMIT_THREADS = 128;
+constexpr int STAGE_CAP = 1024;     // pairs staged per block
+constexpr int WARP_TIER_MAX = 256;  // rows up to this many cells are sorted by one warp
+constexpr int SCAN_TILE = 2048;
+constexpr int HEAVY_SLOTS = 32;
+constexpr int HEAVY_THREADS = 256;
+
+struct OverlapWs {
+  int* zero_begin;   // start of the region that init zeroes
+  size_t zero_ints;  // its length in ints
+  int* row_nnz;      // [R]
+  int* cursor;       // [R]
+  int* pair_count;   // [n_img]
+  int* heavy_count;  // [1]
+  int* tile_sum;     // [n_tiles]
+  int* heavy_rows;   // [heavy_cap]
+  int heavy_cap;
+  int* t_row;        // [cap] temp pairs (per-image regions of cap_img)
+  int* t_col;
+  int* t_cnt;
+  double* t_prior;   // reused as sorted-prior scratch by rowsort
+  int* u_col;        // [cap] row-segmented, unsorted
+  int* u_cnt;
+  double* u_prior;
+  int* d_cnt;        // [HEAVY_SLOTS * ncell] dense scratch of the heavy tier
+  double* d_prior;
+};
+
+size_t carve(OverlapWs& ws, void* base, int n_img, int ncell, int64_t R, int64_t cap) {
+  Carver c(base);
+  int n_tiles = (int)((R + SCAN_TILE - 1) / SCAN_TILE);
+  ws.heavy_cap = (int)(cap / (WARP_TIER_MAX + 1) + 1);
+  ws.row_nnz = c.take<int>(R);
+  ws.zero_begin = ws.row_nnz;
+  ws.cursor = c.take<int>(R);
+  ws.pair_count = c.take<int>(n_img);
+  ws.heavy_count = c.take<int>(1);
+  size_t zero_end = c.off;
+  ws.zero_ints = (zero_end - 0) / sizeof(int);
+  ws.tile_sum = c.take<int>(n_tiles);
+  ws.heavy_rows = c.take<int>(ws.heavy_cap);
+  ws.t_row = c.take<int>(cap);
+  ws.t_col = c.take<int>(cap);
+  ws.t_cnt = c.take<int>(cap);
+  ws.t_prior = c.take<double>(cap);
+  ws.u_col = c.take<int>(cap);
+  ws.u_cnt = c.take<int>(cap);
+  ws.u_prior = c.take<double>(cap);
+  ws.d_cnt = c.take<int>((size_t)HEAVY_SLOTS * ncell);
+  ws.d_prior = c.take<double>((size_t)HEAVY_SLOTS * ncell);
+  return c.used();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void init_kernel(int* zero_begin, size_t zero_ints, int64_t* sum_y, int64_t* sum_x,
+                            int64_t R, int64_t* nnz_flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < zero_ints; k += stride) zero_begin[k] = 0;
+  for (size_t k = i; k < (size_t)R; k += stride) {
+    sum_y[k] = 0;
+    sum_x[k] = 0;
+  }
+  if (i < 4) nnz_flags[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+struct PairStage {
+  int row[STAGE_CAP];
+  int col[STAGE_CAP];
+  int cnt[STAGE_CAP];
+  long long sy[STAGE_CAP];
+  long long sx[STAGE_CAP];
+  double prior[STAGE_CAP];
+  int count;
+  int base;
+};
+
+__device__ __forceinline__ void publish_pair(const OverlapWs& ws, int img, int cap_img, int dst,
+                                             int row, int col, int cnt, long long sy,
+                                             long long sx, double prior, int64_t* sum_y,
+                                             int64_t* sum_x, int64_t* nnz_flags) {
+  atomicAdd(&ws.row_nnz[row], 1);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&sum_y[row]), (unsigned long long)sy);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&sum_x[row]), (unsigned long long)sx);
+  if (dst < cap_img) {
+    size_t t = (size_t)img * cap_img + dst;
+    ws.t_row[t] = row;
+    ws.t_col[t] = col;
+    ws.t_cnt[t] = cnt;
+    ws.t_prior[t] = prior;
+  } else {
+    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+             (unsigned long long)SPALIGN_F_NNZ_OVERFLOW);
+  }
+}
+
+__device__ __forceinline__ void stage_pair(PairStage& st, const OverlapWs& ws, int img,
+                                           int cap_img, int row, int col, int cnt, long long sy,
+                                           long long sx, double prior, int64_t* sum_y,
+                                           int64_t* sum_x, int64_t* nnz_flags) {
+  int pos = atomicAdd(&st.count, 1);
+  if (pos < STAGE_CAP) {
+    st.row[pos] = row;
+    st.col[pos] = col;
+    st.cnt[pos] = cnt;
+    st.sy[pos] = sy;
+    st.sx[pos] = sx;
+    st.prior[pos] = prior;
+  } else {  // stage full (pathological label maps): go straight to global memory
+    int dst = atomicAdd(&ws.pair_count[img], 1);
+    publish_pair(ws, img, cap_img, dst, row, col, cnt, sy, sx, prior, sum_y, sum_x, nnz_flags);
+  }
+}
+
+__device__ __forceinline__ void flush_stage(PairStage& st, const OverlapWs& ws, int img,
+                                            int cap_img, int64_t* sum_y, int64_t* sum_x,
+                                            int64_t* nnz_flags) {
+  __syncthreads();
+  int n = min(st.count, STAGE_CAP);
+  if (threadIdx.x == 0) {
+    st.base = n ? atomicAdd(&ws.pair_count[img], n) : 0;
+    // high-water mark of pairs per image, so a caller can size nnz_cap after an overflow
+    if (n) atomicMax(reinterpret_cast<long long*>(&nnz_flags[2]), (long long)st.base + n);
+  }
+  __syncthreads();
+  int base = st.base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    publish_pair(ws, img, cap_img, base + i, st.row[i], st.col[i], st.cnt[i], st.sy[i],
+                 st.sx[i], st.prior[i], sum_y, sum_x, nnz_flags);
+}
+
+// Fast path: 8x8-pixel cells (DRN stride 8), one thread owns one cell in registers.
+template <typename LabelT>
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
+               const int64_t* __restrict__ sp_off, const double* __restrict__ gy,
+               const double* __restrict__ gx, int cap_img, OverlapWs ws, int64_t* sum_y,
+               int64_t* sum_x, int64_t* nnz_flags) {
+  __shared__ PairStage st;
+  const int img = blockIdx.y;
+  const int ncell = fh * fw;
+  const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  if (threadIdx.x == 0) st.count = 0;
+  __syncthreads();
+  const int64_t row0 = sp_off[img];
+  const int n_sp = (int)(sp_off[img + 1] - row0);
+  if (c < ncell) {
+    const int cy = c / fw, cx = c - cy * fw;
+    const LabelT* p = labels + ((size_t)img * H + (size_t)cy * 8) * W + (size_t)cx * 8;
+    int v[64];
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (sizeof(LabelT) == 4) {
+        int4 a = ld_stream_int4(p + (size_t)r * W);
+        int4 b = ld_stream_int4(p + (size_t)r * W + 4);
+        v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
+        v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
+      } else {
+        const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          longlong2 a = __ldg(q + h);
+          v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;
+          v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+        }
+      }
+    }
+    unsigned mlo = 0, mhi = 0;  // valid-pixel mask
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      mlo |= ((unsigned)v[j] < (unsigned)n_sp) ? (1u << j) : 0u;
+      mhi |= ((unsigned)v[32 + j] < (unsigned)n_sp) ? (1u << j) : 0u;
+    }
+    unsigned long long remaining = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+    bad = remaining != ~0ull;
+    if (bad)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_LABEL_RANGE);
+    double gyl[8], gxl[8];
+    const bool have_prior = gy != nullptr;
+    if (have_prior) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        gyl[k] = gy[cy * 8 + k];
+        gxl[k] = gx[cx * 8 + k];
+      }
+    }
+    while (remaining) {
+      const int i = __ffsll((long long)remaining) - 1;
+      int L = v[0];
+#pragma unroll
+      for (int j = 1; j < 64; ++j) L = (i == j) ? v[j] : L;
+      unsigned lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        lo |= (v[j] == L) ? (1u << j) : 0u;
+        hi |= (v[32 + j] == L) ? (1u << j) : 0u;
+      }
+      const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      const int cnt = __popc(lo) + __popc(hi);
+      int syl = 0, sxl = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) syl += r * __popc((unsigned)(m >> (8 * r)) & 0xffu);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sxl += j * __popcll((m >> j) & 0x0101010101010101ull);
+      double pr = 0.0;
+      if (have_prior) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const unsigned b = (unsigned)(m >> (8 * r)) & 0xffu;
+          double rs = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rs = __dadd_rn(rs, ((b >> j) & 1u) ? gxl[j] : 0.0);
+          pr = __fma_rn(gyl[r], rs, pr);
+        }
+      }
+      stage_pair(st, ws, img, cap_img, (int)(row0 + L), c, cnt,
+                 (long long)cnt * (cy * 8) + syl, (long long)cnt * (cx * 8) + sxl, pr, sum_y,
+                 sum_x, nnz_flags);
+      remaining &= ~m;
+    }
+  }
+  flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
+}
+
+// General path: any H, W, fh, fw.  One thread per cell walks the cell's pixel rectangle once
+// per distinct label (ascending label order).
+template <typename LabelT>
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_generic_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
+                    const int64_t* __restrict__ sp_off, const double* __restrict__ gy,
+                    const double* __restrict__ gx, int cap_img, OverlapWs ws, int64_t* sum_y,
+                    int64_t* sum_x, int64_t* nnz_flags) {
+  __shared__ PairStage st;
+  const int img = blockIdx.y;
+  const int ncell = fh * fw;
+  const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  if (threadIdx.x == 0) st.count = 0;
+  __syncthreads();
+  const int64_t row0 = sp_off[img];
+  const long long n_sp = sp_off[img + 1] - row0;
+  if (c < ncell) {
+    const int cy = c / fw, cx = c - cy * fw;
+    // rows y with floor(y*fh/H) == cy  <=>  y in [ceil(cy*H/fh), ceil((cy+1)*H/fh))
+    const int y0 = (int)(((long long)cy * H + fh - 1) / fh);
+    const int y1 = (int)(((long long)(cy + 1) * H + fh - 1) / fh);
+    const int x0 = (int)(((long long)cx * W + fw - 1) / fw);
+    const int x1 = (int)(((long long)(cx + 1) * W + fw - 1) / fw);
+    const LabelT* base = labels + (size_t)img * H * W;
+    const bool have_prior = gy != nullptr;
+    long long lo = -1;
+    bool bad = false;
+    while (true) {
+      long long cur = 0x7fffffffffffffffLL;
+      int cnt = 0;
+      long long sy = 0, sx = 0;
+      double pr = 0.0;
+      for (int y = y0; y < y1; ++y) {
+        const LabelT* rowp = base + (size_t)y * W;
+        for (int x = x0; x < x1; ++x) {
+          const long long q = (long long)rowp[x];
+          if (q < 0 || q >= n_sp) {
+            bad = true;
+            continue;
+          }
+          if (q > lo) {
+            if (q < cur) {
+              cur = q;
+              cnt = 0;
+              sy = 0;
+              sx = 0;
+              pr = 0.0;
+            }
+            if (q == cur) {
+              ++cnt;
+              sy += y;
+              sx += x;
+              if (have_prior) pr = __dadd_rn(pr, __dmul_rn(gy[y], gx[x]));
+            }
+          }
+        }
+      }
+      if (cur == 0x7fffffffffffffffLL) break;
+      stage_pair(st, ws, img, cap_img, (int)(row0 + cur), c, cnt, sy, sx, pr, sum_y, sum_x,
+                 nnz_flags);
+      lo = cur;
+    }
+    if (bad)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_LABEL_RANGE);
+  }
+  flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
+}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane_id() >= d) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one int per thread across a 256-thread block; returns exclusive prefix,
+// *total receives the block sum
+__device__ __forceinline__ int block_excl_scan_256(int v, int* total) {
+  __shared__ int wsum[8];
+  __shared__ int wtot;
+  int inc = warp_incl_scan(v);
+  if (lane_id() == 31) wsum[warp_id()] = inc;
+  __syncthreads();
+  if (warp_id() == 0) {
+    int w = lane_id() < 8 ? wsum[lane_id()] : 0;
+    int winc = warp_incl_scan(w);
+    if (lane_id() < 8) wsum[lane_id()] = winc - w;
+    if (lane_id() == 7) wtot = winc;
+  }
+  __syncthreads();
+  int excl = inc - v + wsum[warp_id()];
+  *total = wtot;
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(256)
+scan_tile_sums_kernel(const int* __restrict__ row_nnz, int64_t R, int* tile_sum) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_TILE / 256; ++k) {
+    int64_t idx = base + k * 256 + threadIdx.x;
+    if (idx < R) s += row_nnz[idx];
+  }
+  int total;
+  block_excl_scan_256(s, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+scan_finish_kernel(const int* __restrict__ row_nnz, int64_t R, const int* __restrict__ tile_sum,
+                   int n_tiles, int* indptr, int64_t* nnz_flags, int64_t nnz_cap,
+                   int* heavy_rows, int* heavy_count, int heavy_cap) {
+  __shared__ long long s_prefix;
+  // prefix of the tiles before this one
+  long long pre = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) pre += tile_sum[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+  __shared__ long long wpre[8];
+  if (lane_id() == 0) wpre[warp_id()] = pre;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < 8; ++i) t += wpre[i];
+    s_prefix = t;
+  }
+  __syncthreads();
+  const long long prefix = s_prefix;
+  constexpr int PER = SCAN_TILE / 256;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * PER;
+  int vals[PER];
+  int tsum = 0;
+  bool empty = false;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    int64_t idx = base + k;
+    vals[k] = idx < R ? row_nnz[idx] : 0;
+    if (idx < R && vals[k] == 0) empty = true;
+    tsum += vals[k];
+  }
+  int total;
+  int excl = block_excl_scan_256(tsum, &total);
+  long long run = prefix + excl;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    int64_t idx = base + k;
+    if (idx < R) {
+      indptr[idx] = (int)run;
+      if (vals[k] > WARP_TIER_MAX) {
+        int h = atomicAdd(heavy_count, 1);
+        if (h < heavy_cap) heavy_rows[h] = (int)idx;
+      }
+    }
+    run += vals[k];
+  }
+  if (empty)
+    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+             (unsigned long long)SPALIGN_F_EMPTY_ROW);
+  if ((int)blockIdx.x == n_tiles - 1 && threadIdx.x == 0) {
+    long long nnz = prefix + total;
+    nnz_flags[0] = nnz;
+    indptr[R] = (int)(nnz > 0x7fffffffLL ? 0x7fffffffLL : nnz);
+    if (nnz > nnz_cap)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_NNZ_OVERFLOW);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scatter_kernel(OverlapWs ws, int cap_img, const int* __restrict__ indptr, int64_t nnz_cap,
+               const int64_t* __restrict__ nnz_flags) {
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
+  const int img = blockIdx.y;
+  const int n = min(ws.pair_count[img], cap_img);
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < n; t += gridDim.x * 256) {
+    const size_t src = (size_t)img * cap_img + t;
+    const int r = ws.t_row[src];
+    const int pos = indptr[r] + atomicAdd(&ws.cursor[r], 1);
+    if (pos < nnz_cap) {
+      ws.u_col[pos] = ws.t_col[src];
+      ws.u_cnt[pos] = ws.t_cnt[src];
+      ws.u_prior[pos] = ws.t_prior[src];
+    }
+  }
+}
+
+// one warp per row with <= WARP_TIER_MAX cells: rank sort by cell id
+__global__ void __launch_bounds__(256)
+rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int* indices,
+                    int* counts, int* area, double* sum_prior,
+                    const int64_t* __restrict__ nnz_flags) {
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
+  if (r >= R) return;
+  const int lane = lane_id();
+  const int base = indptr[r];
+  const int L = indptr[r + 1] - base;
+  if (L > WARP_TIER_MAX) return;
+  int a_sum = 0;
+  double* sorted_prior = ws.t_prior;  // pairs are dead after scatter
+  for (int a = 0; a < L; a += 32) {
+    const int e = a + lane;
+    const bool valid = e < L;
+    const int myc = valid ? ws.u_col[base + e] : 0x7fffffff;
+    int rank = 0;
+    for (int b = 0; b < L; b += 32) {
+      const int oc = (b + lane < L) ? ws.u_col[base + b + lane] : 0x7fffffff;
+      const int nb = min(32, L - b);
+      for (int j = 0; j < nb; ++j) {
+        const int o = __shfl_sync(0xffffffffu, oc, j);
+        rank += (o < myc) ? 1 : 0;
+      }
+    }
+    if (valid) {
+      const int cn = ws.u_cnt[base + e];
+      indices[base + rank] = myc;
+      counts[base + rank] = cn;
+      sorted_prior[base + rank] = ws.u_prior[base + e];
+      a_sum += cn;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
+  if (lane == 0) area[r] = a_sum;
+  if (sum_prior != nullptr) {
+    __syncwarp();
+    double ps = 0.0;
+    for (int e = lane; e < L; e += 32) ps = __dadd_rn(ps, sorted_prior[base + e]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, d));
+    if (lane == 0) sum_prior[r] = ps;
+  }
+}
+
+// rows longer than WARP_TIER_MAX: scatter into a dense per-cell array, compact in order
+__global__ void __launch_bounds__(HEAVY_THREADS)
+rowsort_heavy_kernel(OverlapWs ws, const int* __restrict__ indptr, int ncell, int* indices,
+                     int* counts, int* area, double* sum_prior,
+                     const int64_t* __restrict__ nnz_flags) {
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
+  const int n_heavy = min(*ws.heavy_count, ws.heavy_cap);
+  int* d_cnt = ws.d_cnt + (size_t)blockIdx.x * ncell;
+  double* d_prior = ws.d_prior + (size_t)blockIdx.x * ncell;
+  __shared__ double red_p[HEAVY_THREADS];
+  __shared__ int red_a[HEAVY_THREADS];
+  for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const int r = ws.heavy_rows[h];
+    const int base = indptr[r];
+    const int L = indptr[r + 1] - base;
+    for (int c = threadIdx.x; c < ncell; c += HEAVY_THREADS) d_cnt[c] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < L; e += HEAVY_THREADS) {
+      const int c = ws.u_col[base + e];
+      d_cnt[c] = ws.u_cnt[base + e];
+      d_prior[c] = ws.u_prior[base + e];
+    }
+    __syncthreads();
+    int running = 0;
+    int a_sum = 0;
+    double p_sum = 0.0;
+    for (int c0 = 0; c0 < ncell; c0 += HEAVY_THREADS) {
+      const int c = c0 + threadIdx.x;
+      const int cn = c < ncell ? d_cnt[c] : 0;
+      const int flag = cn > 0 ? 1 : 0;
+      int total;
+      const int excl = block_excl_scan_256(flag, &total);
+      if (flag) {
+        indices[base + running + excl] = c;
+        counts[base + running + excl] = cn;
+        a_sum += cn;
+        p_sum = __dadd_rn(p_sum, d_prior[c]);
+      }
+      running += total;
+    }
+    red_p[threadIdx.x] = p_sum;
+    red_a[threadIdx.x] = a_sum;
+    __syncthreads();
+    for (int s = HEAVY_THREADS / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        red_p[threadIdx.x] = __dadd_rn(red_p[threadIdx.x], red_p[threadIdx.x + s]);
+        red_a[threadIdx.x] += red_a[threadIdx.x + s];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      area[r] = red_a[0];
+      if (sum_prior != nullptr) sum_prior[r] = red_p[0];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename LabelT>
+__global__ void __launch_bounds__(256)
+label_max_kernel(const LabelT* __restrict__ labels, int64_t n_pix, int32_t* max_out) {
+  const int img = blockIdx.y;
+  const LabelT* p = labels + (size_t)img * n_pix;
+  long long m = -1;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pix;
+       i += (int64_t)gridDim.x * 256) {
+    long long q = (long long)p[i];
+    m = q > m ? q : m;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    long long o = __shfl_xor_sync(0xffffffffu, m, d);
+    m = o > m ? o : m;
+  }
+  if (lane_id() == 0) {
+    if (m > 0x7ffffffeLL) m = 0x7ffffffeLL;
+    atomicMax(&max_out[img], (int)m);
+  }
+}
+
+}  // namespace
+}  // namespace spalign
+
+using namespace spalign;
+
+extern "C" int spalign_label_max(const void* labels, int label_dtype, int n_img, int H, int W,
+                                 int32_t* max_out, spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(labels && max_out && n_img > 0 && H > 0 && W > 0, "label_max: bad arguments");
+  SPALIGN_REQUIRE(label_dtype == SPALIGN_I32 || label_dtype == SPALIGN_I64,
+                  "label_max: label_dtype must be I32 or I64");
+  SPALIGN_CUDA(cudaMemsetAsync(max_out, 0xff, sizeof(int32_t) * n_img, stream));
+  const int64_t n_pix = (int64_t)H * W;
+  int gx = (int)((n_pix + 256 * 16 - 1) / (256 * 16));
+  gx = gx < 1 ? 1 : (gx > 4 * kNumSMs ? 4 * kNumSMs : gx);
+  dim3 grid(gx, n_img);
+  if (label_dtype == SPALIGN_I32)
+    label_max_kernel<int32_t><<<grid, 256, 0, stream>>>((const int32_t*)labels, n_pix, max_out);
+  else
+    label_max_kernel<int64_t><<<grid, 256, 0, stream>>>((const int64_t*)labels, n_pix, max_out);
+  return check_launch("label_max");
+}
+
+extern "C" size_t spalign_overlap_workspace_bytes(int n_img, int H, int W, int fh, int fw,
+                                                  int64_t n_rows, int64_t nnz_cap) {
+  (void)H;
+  (void)W;
+  OverlapWs ws;
+  return carve(ws, nullptr, n_img, fh * fw, n_rows, nnz_cap) + 256;
+}
+
+extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_img, int H, int W,
+                                   int fh, int fw, const int64_t* sp_off, int64_t n_rows,
+                                   const double* gy, const double* gx, int64_t nnz_cap,
+                                   int32_t* indptr, int32_t* indices, int32_t* counts,
+                                   int32_t* area, int64_t* sum_y, int64_t* sum_x,
+                                   double* sum_prior, int64_t* nnz_flags, void* workspace,
+                                   size_t ws_bytes, spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(labels && sp_off && indptr && indices && counts && area && sum_y && sum_x &&
+                      nnz_flags && workspace,
+                  "overlap_csr: NULL argument");
+  SPALIGN_REQUIRE(n_img > 0 && H > 0 && W > 0 && fh > 0 && fw > 0 && n_rows > 0,
+                  "overlap_csr: bad shape");
+  SPALIGN_REQUIRE(label_dtype == SPALIGN_I32 || label_dtype == SPALIGN_I64,
+                  "overlap_csr: label_dtype must be I32 or I64");
+  SPALIGN_REQUIRE((gy == nullptr) == (gx == nullptr), "overlap_csr: gy and gx go together");
+  SPALIGN_REQUIRE(sum_prior == nullptr || gy != nullptr, "overlap_csr: sum_prior needs gy/gx");
+  SPALIGN_REQUIRE(n_rows < 0x7fffffffLL && nnz_cap > 0 && nnz_cap < 0x7fffffffLL,
+                  "overlap_csr: n_rows / nnz_cap must fit int32");
+  SPALIGN_REQUIRE((int64_t)fh * fw < 0x7fffffffLL, "overlap_csr: too many cells");
+  const int cap_img = (int)(nnz_cap / n_img);
+  SPALIGN_REQUIRE(cap_img > 0, "overlap_csr: nnz_cap smaller than n_img");
+  const int ncell = fh * fw;
+  OverlapWs ws;
+  size_t need = carve(ws, nullptr, n_img, ncell, n_rows, nnz_cap) + 256;
+  if (ws_bytes < need) {
+    set_error("overlap_csr: workspace %zu < %zu bytes", ws_bytes, need);
+    return SPALIGN_E_WORKSPACE;
+  }
+  void* aligned = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  carve(ws, aligned, n_img, ncell, n_rows, nnz_cap);
+
+  init_kernel<<<2 * kNumSMs, 256, 0, stream>>>(ws.zero_begin, ws.zero_ints, sum_y, sum_x, n_rows,
+                                               nnz_flags);
+  dim3 egrid((ncell + EMIT_THREADS - 1) / EMIT_THREADS, n_img);
+  const bool s8 = (H == 8 * fh) && (W == 8 * fw) &&
+                  (reinterpret_cast<size_t>(labels) % 16 == 0);
+  if (label_dtype == SPALIGN_I32) {
+    if (s8)
+      emit_s8_kernel<int32_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+          (const int32_t*)labels, H, W, fh, fw, sp_off, gy, gx, cap_img, ws, sum_y, sum_x,
+          nnz_flags);
+    else
+      emit_generic_kernel<int32_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+          (const int32_t*)labels, H, W, fh, fw, sp_off, gy, gx, cap_img, ws, sum_y, sum_x,
+          nnz_flags);
+  } else {
+    if (s8)
+      emit_s8_kernel<int64_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+          (const int64_t*)labels, H, W, fh, fw, sp_off, gy, gx, cap_img, ws, sum_y, sum_x,
+          nnz_flags);
+    else
+      emit_generic_kernel<int64_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+          (const int64_t*)labels, H, W, fh, fw, sp_off, gy, gx, cap_img, ws, sum_y, sum_x,
+          nnz_flags);
+  }
+  const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
+  scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum);
+  scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum, n_tiles,
+                                                  indptr, nnz_flags, nnz_cap, ws.heavy_rows,
+                                                  ws.heavy_count, ws.heavy_cap);
+  int sgx = (cap_img + 256 * 4 - 1) / (256 * 4);
+  sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
+  scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
+  rowsort_warp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
+      ws, indptr, n_rows, indices, counts, area, sum_prior, nnz_flags);
+  rowsort_heavy_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(ws, indptr, ncell, indices,
+                                                                 counts, area, sum_prior,
+                                                                 nnz_flags);
+  return check_launch("overlap_csr");
+}

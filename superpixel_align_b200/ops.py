@@ -1,0 +1,453 @@
+"""Thin torch-tensor wrappers over the C ABI (include/spalign.h).
+
+torch is the carrier only (device memory, streams): every function here enqueues hand-written
+sm_100a kernels from libspalign_b200.so on the current CUDA stream and returns device tensors.
+Nothing in this module synchronises unless its docstring says so.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
+
+# kernel launches per entry point (kept in sync with csrc/*.cu)
+_LAUNCH_COST = dict(label_max=1, overlap_csr=7, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
+                    kmeans_sweep=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
+                    refine=2, confusion2=1)
+
+
+def _count(name):
+    global LAUNCHES
+    LAUNCHES += _LAUNCH_COST[name]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _label_code(t):
+    if t.dtype == torch.int32:
+        return _lib.I32
+    if t.dtype == torch.int64:
+        return _lib.I64
+    raise TypeError('label maps must be int32 or int64, got %s' % t.dtype)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SpalignError('spalign ops need CUDA tensors (there is no CPU fallback)')
+
+
+# --------------------------------------------------------------------------------------
+def label_max(labels: torch.Tensor) -> torch.Tensor:
+    """Per-image maximum label, int32 [n_img] (n_superpixels = max + 1)."""
+    _require_cuda(labels)
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    out = torch.empty(n, dtype=torch.int32, device=labels.device)
+    check(_lib.load().spalign_label_max(_ptr(labels), _label_code(labels), n, H, W, _ptr(out),
+                                        _stream()), 'label_max')
+    _count('label_max')
+    return out
+
+
+def prior_axes(H, W, y_rel_pos, x_rel_pos, y_rel_sigma, x_rel_sigma):
+    """Separable factors of the Gaussian road prior (batch_spalign_kmeans.py:111-122):
+    w(y, x) = gy[y] * gx[x].  Host float64 (H + W exps)."""
+    ymean, xmean = int(H * y_rel_pos), int(W * x_rel_pos)
+    ys, xs = H * y_rel_sigma, W * x_rel_sigma
+    gy = np.exp(-((np.arange(H) - ymean) ** 2 / (2 * ys) ** 2))
+    gx = np.exp(-((np.arange(W) - xmean) ** 2 / (2 * xs) ** 2))
+    return gy, gx
+
+
+@dataclass
+class Overlap:
+    """CSR overlap matrix of a batch + per-superpixel statistics (device tensors)."""
+    indptr: torch.Tensor      # int32 [n_rows+1]
+    indices: torch.Tensor     # int32 [nnz_cap] (first nnz valid), cell id within the image
+    counts: torch.Tensor      # int32 [nnz_cap]
+    area: torch.Tensor        # int32 [n_rows]
+    sum_y: torch.Tensor       # int64 [n_rows]
+    sum_x: torch.Tensor       # int64 [n_rows]
+    sum_prior: Optional[torch.Tensor]  # float64 [n_rows]
+    nnz_flags: torch.Tensor   # int64 [4]
+    sp_off: torch.Tensor      # int64 [n_img+1] device
+    sp_off_host: np.ndarray   # int64 [n_img+1]
+    n_img: int
+    H: int
+    W: int
+    fh: int
+    fw: int
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.sp_off_host[-1])
+
+    @property
+    def max_rows(self) -> int:
+        return int(np.diff(self.sp_off_host).max())
+
+    def validate(self):
+        """Synchronises.  Raises on label-range / capacity problems; returns nnz."""
+        nnz, flags, hw, _ = self.nnz_flags.tolist()
+        if flags & _lib.F_NNZ_OVERFLOW:
+            raise OverflowError('overlap CSR capacity exceeded (nnz=%d, per-image high water %d)'
+                                % (nnz, hw))
+        if flags & _lib.F_LABEL_RANGE:
+            raise ValueError('label map holds ids outside [0, n_superpixels)')
+        return nnz
+
+    @property
+    def has_empty_rows(self) -> bool:
+        return bool(self.nnz_flags[1].item() & _lib.F_EMPTY_ROW)
+
+    def weights(self) -> torch.Tensor:
+        """Mean prior per superpixel, float64 (create_prior, batch_spalign_kmeans.py:124-127)."""
+        return self.sum_prior / self.area.to(torch.float64)
+
+
+def overlap_csr(labels: torch.Tensor, fh: int, fw: int, n_sp: Sequence[int],
+                prior: Optional[Sequence[float]] = None, nnz_cap_per_image: Optional[int] = None,
+                retry: bool = False) -> Overlap:
+    """K1.  labels [n_img, H, W] int32/int64 CUDA; n_sp = superpixels per image (host ints).
+
+    ``prior`` = (y_rel_pos, x_rel_pos, y_rel_sigma, x_rel_sigma) also accumulates the prior.
+    With ``retry`` the call synchronises and re-runs once with a larger capacity on overflow.
+    """
+    _require_cuda(labels)
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    dev = labels.device
+    n_sp = np.asarray(n_sp, dtype=np.int64).reshape(-1)
+    assert len(n_sp) == n, 'one superpixel count per image'
+    sp_off_host = np.concatenate([[0], np.cumsum(n_sp)]).astype(np.int64)
+    n_rows = int(sp_off_host[-1])
+    sp_off = torch.from_numpy(sp_off_host).to(dev, non_blocking=True)
+    ncell = fh * fw
+    if nnz_cap_per_image is None:
+        nnz_cap_per_image = min(H * W, 3 * ncell + 2 * int(n_sp.max()) + 1024)
+    cap = int(nnz_cap_per_image) * n
+    gy = gx = None
+    if prior is not None:
+        gy_h, gx_h = prior_axes(H, W, *prior)
+        gy = torch.from_numpy(gy_h).to(dev, non_blocking=True)
+        gx = torch.from_numpy(gx_h).to(dev, non_blocking=True)
+    lib = _lib.load()
+    ws_bytes = lib.spalign_overlap_workspace_bytes(n, H, W, fh, fw, n_rows, cap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    i64 = dict(dtype=torch.int64, device=dev)
+    ov = Overlap(
+        indptr=torch.empty(n_rows + 1, **i32), indices=torch.empty(cap, **i32),
+        counts=torch.empty(cap, **i32), area=torch.empty(n_rows, **i32),
+        sum_y=torch.empty(n_rows, **i64), sum_x=torch.empty(n_rows, **i64),
+        sum_prior=torch.empty(n_rows, dtype=torch.float64, device=dev) if prior is not None else None,
+        nnz_flags=torch.empty(4, **i64), sp_off=sp_off, sp_off_host=sp_off_host, n_img=n, H=H,
+        W=W, fh=fh, fw=fw)
+    check(lib.spalign_overlap_csr(
+        _ptr(labels), _label_code(labels), n, H, W, fh, fw, _ptr(sp_off), n_rows, _ptr(gy),
+        _ptr(gx), cap, _ptr(ov.indptr), _ptr(ov.indices), _ptr(ov.counts), _ptr(ov.area),
+        _ptr(ov.sum_y), _ptr(ov.sum_x), _ptr(ov.sum_prior), _ptr(ov.nnz_flags), _ptr(ws),
+        ws_bytes, _stream()), 'overlap_csr')
+    _count('overlap_csr')
+    ov._keepalive = (ws, gy, gx, labels)  # stream-ordered reuse is safe, but keep it simple
+    if retry:
+        nnz, flags, hw, _ = ov.nnz_flags.tolist()
+        if flags & _lib.F_NNZ_OVERFLOW:
+            bigger = min(H * W, max(2 * nnz_cap_per_image, int(hw) + 1024, int(nnz) // n + 1024))
+            if bigger <= nnz_cap_per_image:
+                raise OverflowError('overlap CSR capacity exceeded at the maximum capacity')
+            return overlap_csr(labels, fh, fw, n_sp, prior, bigger, retry=True)
+    return ov
+
+
+# --------------------------------------------------------------------------------------
+def as_cellmajor(feature_maps: torch.Tensor) -> torch.Tensor:
+    """[n, C, fh, fw] (any memory format) -> [n, fh*fw, C] contiguous float32.
+
+    channels_last input is a zero-copy view; NCHW input goes through the transpose kernel."""
+    _require_cuda(feature_maps)
+    assert feature_maps.dim() == 4
+    n, C, fh, fw = feature_maps.shape
+    if feature_maps.dtype != torch.float32:
+        feature_maps = feature_maps.float()
+    nhwc = feature_maps.permute(0, 2, 3, 1)
+    if nhwc.is_contiguous():
+        return nhwc.reshape(n, fh * fw, C)
+    src = feature_maps.contiguous()
+    dst = torch.empty((n, fh * fw, C), dtype=torch.float32, device=src.device)
+    check(_lib.load().spalign_nchw_to_cellmajor(_ptr(src), _ptr(dst), n, C, fh * fw, _stream()),
+          'nchw_to_cellmajor')
+    _count('nchw_to_cellmajor')
+    return dst
+
+
+def padded_ld(d: int) -> int:
+    """Row stride (floats) used for descriptor matrices: multiple of 4 floats (16 bytes)."""
+    return (d + 3) // 4 * 4
+
+
+def pool(feat_cellmajor: torch.Tensor, ov: Overlap, append_pos: bool = True,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K2.  feat [n_img, fh*fw, C] float32 cell-major -> descriptors [n_rows, C(+2)] float32
+    (a view of a [n_rows, ld] buffer with ld = padded_ld(C+2); pad columns are zero)."""
+    _require_cuda(feat_cellmajor)
+    n, ncell, C = feat_cellmajor.shape
+    assert n == ov.n_img and ncell == ov.fh * ov.fw and feat_cellmajor.is_contiguous()
+    D = C + (2 if append_pos else 0)
+    ld = padded_ld(D)
+    if out is None:
+        out = torch.empty((ov.n_rows, ld), dtype=torch.float32, device=feat_cellmajor.device)
+    assert out.shape == (ov.n_rows, ld) and out.is_contiguous()
+    check(_lib.load().spalign_pool(
+        _ptr(feat_cellmajor), n, C, ov.fh, ov.fw, _ptr(ov.sp_off), ov.n_rows, ov.max_rows,
+        _ptr(ov.indptr), _ptr(ov.indices), _ptr(ov.counts), _ptr(ov.area), _ptr(ov.sum_y),
+        _ptr(ov.sum_x), int(append_pos), _ptr(out), ld, _stream()), 'pool')
+    _count('pool')
+    return out[:, :D]
+
+
+# --------------------------------------------------------------------------------------
+def _x_code(X):
+    if X.dtype == torch.float32:
+        return _lib.F32, 4
+    if X.dtype == torch.float64:
+        return _lib.F64, 8
+    raise TypeError('k-means rows must be float32 or float64')
+
+
+def as_kmeans_rows(X: torch.Tensor) -> torch.Tensor:
+    """Return a [N, Dr] view whose row stride is a multiple of 16 bytes and base 16-byte
+    aligned (copying into a padded buffer when needed)."""
+    _require_cuda(X)
+    assert X.dim() == 2
+    code, es = _x_code(X)
+    per16 = 16 // es
+    ok = (X.stride(1) == 1 and X.stride(0) % per16 == 0 and X.data_ptr() % 16 == 0
+          and X.stride(0) >= (X.shape[1] + per16 - 1) // per16 * per16)
+    if ok:
+        return X
+    ld = (X.shape[1] + per16 - 1) // per16 * per16
+    buf = torch.zeros((X.shape[0], ld), dtype=X.dtype, device=X.device)
+    buf[:, :X.shape[1]] = X
+    return buf[:, :X.shape[1]]
+
+
+@dataclass
+class KMeansResult:
+    assign: torch.Tensor   # int32 [N]
+    iters: torch.Tensor    # int32 [G]
+    status: torch.Tensor   # int32 [G]
+    centers: Optional[torch.Tensor]  # float64 [G, K, D]
+
+
+def kmeans_groups(X: torch.Tensor, w: torch.Tensor, init_assign: torch.Tensor, K: int,
+                  group_off: torch.Tensor, n_iter: int = 1000, pos_grid=None,
+                  want_centers: bool = False) -> KMeansResult:
+    """K3, one persistent CTA per group: the whole iteration loop runs on the device.
+
+    X [N, Dr] float32/float64 (row stride multiple of 16 B), w [N] float64, init_assign [N]
+    int32 (copied), group_off [G+1] int64 device.  ``pos_grid=(fh, fw)`` appends the virtual
+    (x, y) cell-index columns of direct_clustering.py:297-303."""
+    _require_cuda(X, w, init_assign, group_off)
+    X = as_kmeans_rows(X)
+    code, _ = _x_code(X)
+    N, Dr = X.shape
+    D = Dr + (2 if pos_grid else 0)
+    G = group_off.numel() - 1
+    dev = X.device
+    assign = init_assign.to(torch.int32).clone().contiguous()
+    w = w.to(torch.float64).contiguous()
+    iters = torch.empty(G, dtype=torch.int32, device=dev)
+    status = torch.empty(G, dtype=torch.int32, device=dev)
+    centers = torch.empty((G, K, D), dtype=torch.float64, device=dev) if want_centers else None
+    pos_w = pos_grid[1] if pos_grid else 0
+    pos_period = pos_grid[0] * pos_grid[1] if pos_grid else 0
+    check(_lib.load().spalign_kmeans_groups(
+        _ptr(X), code, X.stride(0), 1 if pos_grid else 0, pos_w, pos_period, _ptr(w), D, K,
+        n_iter, _ptr(group_off), G, _ptr(assign), _ptr(centers), _ptr(iters), _ptr(status), None,
+        0, _stream()), 'kmeans_groups')
+    _count('kmeans_groups')
+    return KMeansResult(assign, iters, status, centers)
+
+
+class KMeansLarge:
+    """K3 for large groups: multi-CTA sweeps driven from the host, one step per iteration.
+
+    ``step()`` enqueues sweep -> reduce -> [all-reduce hook] -> update.  ``run()`` loops and
+    polls the stop flags every ``poll`` iterations (one small D2H).  Used for joint batches,
+    direct cell clustering and (with ``allreduce``) the multi-GPU global clustering.
+    """
+
+    TILE = 32
+
+    def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
+                 pos_row0=0, chunks_per_group=None, allreduce=None):
+        _require_cuda(X, w, init_assign)
+        self.X = as_kmeans_rows(X)
+        self.code, _ = _x_code(self.X)
+        self.N, Dr = self.X.shape
+        self.K, self.n_iter = K, n_iter
+        self.D = Dr + (2 if pos_grid else 0)
+        self.pos_mode = 1 if pos_grid else 0
+        self.pos_w = pos_grid[1] if pos_grid else 0
+        self.pos_period = pos_grid[0] * pos_grid[1] if pos_grid else 0
+        self.pos_row0 = pos_row0
+        self.allreduce = allreduce
+        dev = self.X.device
+        self.w = w.to(torch.float64).contiguous()
+        self.assign = init_assign.to(torch.int32).clone().contiguous()
+        goff = np.asarray(group_off_host, dtype=np.int64)
+        self.G = len(goff) - 1
+        chunks, gco = [], [0]
+        for g in range(self.G):
+            r0, r1 = int(goff[g]), int(goff[g + 1])
+            n = r1 - r0
+            tiles = max(1, math.ceil(n / self.TILE))
+            want = chunks_per_group or min(max(1, tiles // 4), max(1, (2 * 148) // self.G))
+            want = max(1, min(want, tiles))
+            per = math.ceil(tiles / want) * self.TILE
+            if n == 0:
+                chunks.append((g, r0, r0))
+            else:
+                for r in range(r0, r1, per):
+                    chunks.append((g, r, min(r + per, r1)))
+            gco.append(len(chunks))
+        self.n_chunks = len(chunks)
+        self.chunks = torch.tensor(chunks, dtype=torch.int64, device=dev).reshape(-1, 3)
+        self.gco = torch.tensor(gco, dtype=torch.int32, device=dev)
+        self.pv = K * (self.D + 2) + 1
+        self.partials = torch.zeros((self.n_chunks, self.pv), dtype=torch.float64, device=dev)
+        self.totals = torch.zeros((self.G, self.pv), dtype=torch.float64, device=dev)
+        self.centers = torch.zeros((self.G, K, self.D), dtype=torch.float64, device=dev)
+        self.iters = torch.zeros(self.G, dtype=torch.int32, device=dev)
+        self.status = torch.full((self.G,), _lib.KM_RUNNING, dtype=torch.int32, device=dev)
+        self._lib = _lib.load()
+        self._init_done = False
+
+    def _sweep(self, mode):
+        check(self._lib.spalign_kmeans_sweep(
+            _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
+            self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
+            self.n_chunks, _ptr(self.centers), mode, _ptr(self.assign), _ptr(self.status),
+            _ptr(self.partials), _stream()), 'kmeans_sweep')
+        _count('kmeans_sweep')
+        check(self._lib.spalign_kmeans_reduce(_ptr(self.partials), _ptr(self.gco), self.G, self.D,
+                                              self.K, _ptr(self.totals), _stream()),
+              'kmeans_reduce')
+        _count('kmeans_reduce')
+        if self.allreduce is not None:
+            self.allreduce(self.totals)
+        check(self._lib.spalign_kmeans_update(_ptr(self.totals), self.G, self.D, self.K, mode,
+                                              self.n_iter, _ptr(self.centers), _ptr(self.iters),
+                                              _ptr(self.status), _stream()), 'kmeans_update')
+        _count('kmeans_update')
+
+    def init_centers(self):
+        self._sweep(0)
+        self._init_done = True
+
+    def step(self):
+        if not self._init_done:
+            self.init_centers()
+        self._sweep(1)
+
+    def run(self, poll: int = 4) -> KMeansResult:
+        """Synchronises every ``poll`` iterations to read the stop flags."""
+        if not self._init_done:
+            self.init_centers()
+        done = 0
+        while done < self.n_iter:
+            for _ in range(min(poll, self.n_iter - done)):
+                self._sweep(1)
+            done += poll
+            if bool((self.status != _lib.KM_RUNNING).all().item()):
+                break
+        if self.n_iter == 0:
+            self.status.fill_(_lib.KM_ITER_CAP)
+        return KMeansResult(self.assign, self.iters, self.status, self.centers)
+
+
+def kmeans_init_device(w: torch.Tensor, group_off: torch.Tensor, shuffled: torch.Tensor,
+                       shuf_off: torch.Tensor):
+    """Seeded init on the device for groups of <= 4096 rows.  Returns (assign int32 [N],
+    m int32 [G]); m[g] != len(shuffled_g) means prior-weight ties changed the split size and
+    the host must redo that group's init (m[g] == -1: group too large)."""
+    _require_cuda(w, group_off, shuffled, shuf_off)
+    G = group_off.numel() - 1
+    assign = torch.empty(w.numel(), dtype=torch.int32, device=w.device)
+    m = torch.empty(G, dtype=torch.int32, device=w.device)
+    check(_lib.load().spalign_kmeans_init(_ptr(w), _ptr(group_off), G, _ptr(shuffled),
+                                          _ptr(shuf_off), _ptr(assign), _ptr(m), _stream()),
+          'kmeans_init')
+    _count('kmeans_init')
+    return assign, m
+
+
+# --------------------------------------------------------------------------------------
+_OUT_CODES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
+
+
+def paint(labels: torch.Tensor, sp_off: torch.Tensor, table: torch.Tensor,
+          out_dtype: Optional[torch.dtype] = torch.uint8, want_mask: bool = True,
+          road_value: int = 0):
+    """K4: cluster_map[p] = table[sp_off[img] + label[p]], road_mask = (cluster_map == road_value).
+    Returns (cluster_map or None, road_mask uint8 or None)."""
+    _require_cuda(labels, sp_off, table)
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    dev = labels.device
+    table = table.to(torch.int32).contiguous()
+    cmap = torch.empty((n, H, W), dtype=out_dtype, device=dev) if out_dtype is not None else None
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    check(_lib.load().spalign_paint(
+        _ptr(labels), _label_code(labels), n, H, W, _ptr(sp_off), _ptr(table), _ptr(cmap),
+        _OUT_CODES[out_dtype] if out_dtype is not None else _lib.U8, _ptr(mask), road_value,
+        _stream()), 'paint')
+    _count('paint')
+    return cmap, mask
+
+
+def refine(ov: Overlap, road_cell: torch.Tensor, thr: float):
+    """K5: per-superpixel overlap with a cell-level road mask [n_img, fh, fw] (bool/uint8).
+    Returns (overlap int64 [n_rows], road_px int64 [n_img], keep int32 [n_rows])."""
+    _require_cuda(road_cell)
+    dev = road_cell.device
+    rc = road_cell.to(torch.uint8).contiguous().reshape(ov.n_img, -1)
+    overlap = torch.empty(ov.n_rows, dtype=torch.int64, device=dev)
+    road_px = torch.empty(ov.n_img, dtype=torch.int64, device=dev)
+    keep = torch.empty(ov.n_rows, dtype=torch.int32, device=dev)
+    check(_lib.load().spalign_refine(
+        _ptr(ov.sp_off), ov.n_img, ov.n_rows, ov.fh * ov.fw, ov.max_rows, _ptr(ov.indptr),
+        _ptr(ov.indices), _ptr(ov.counts), _ptr(rc), float(thr), _ptr(overlap), _ptr(road_px),
+        _ptr(keep), _stream()), 'refine')
+    _count('refine')
+    return overlap, road_px, keep
+
+
+def confusion2(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """2-class confusion per image: conf[img, gt, pred] over pixels with gt >= 0
+    (chainercv semantics used at batch_spalign_kmeans.py:398-402).  int64 [n_img, 2, 2]."""
+    _require_cuda(pred, gt)
+    n = pred.shape[0]
+    pred = pred.to(torch.uint8).contiguous().reshape(n, -1)
+    gt = gt.to(torch.int32).contiguous().reshape(n, -1)
+    conf = torch.empty((n, 2, 2), dtype=torch.int64, device=pred.device)
+    check(_lib.load().spalign_confusion2(_ptr(pred), _ptr(gt), n, pred.shape[1], _ptr(conf),
+                                         _stream()), 'confusion2')
+    _count('confusion2')
+    return conf

@@ -1,0 +1,162 @@
+"""GPU tests of the reference-facing drop-in modules: they are called the way the reference's
+estimate_road_mask calls its own functions (NumPy in, NumPy out, an argparse-like ``args``)
+and compared with the oracle / the golden vectors frozen from the reference."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import spalign_oracle as so  # noqa: E402
+from superpixel_align_b200 import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(**kw):
+    base = dict(gpu=0, n_clusters=4, n_anchors=10, n_neighbors=4, without_pos=False, y_rel_pos=0.75,
+                x_rel_pos=0.5, y_rel_sigma=0.1, x_rel_sigma=0.1, overlap_threshold=0.01)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.fixture()
+def batch():
+    H, W, fh, fw, C = 128, 256, 16, 32, 32
+    labs = np.stack([synth.voronoi_labels(H, W, 6, 10, image_index=i, dtype=np.int64) for i in range(3)])
+    feats = np.stack([synth.smooth_features(C, fh, fw, seed=i) for i in range(3)])
+    imgs = np.zeros((3, 3, H, W), dtype=np.float32)
+    return labs, feats, imgs
+
+
+def test_spalign_dropin_matches_oracle_end_to_end(batch):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    labs, feats, imgs = batch
+    args = _args()
+    bsk.clear_cache()
+    f, n_per = bsk.batch_superpixel_align(args, None, imgs, labs, feats)
+    assert n_per == [60, 60, 60] and f.shape == (180, 34) and f.dtype == np.float64
+    w = bsk.batch_create_prior(args, labs)
+    assert w.shape == (180,) and w.dtype == np.float64
+    np.random.seed(1111)
+    cres, road = bsk.batch_weighted_kmeans(args, labs, f, w, n_per)
+    assert cres.shape == labs.shape and cres.dtype == labs.dtype and road.dtype == bool
+    # oracle on the same inputs
+    of, ow = [], []
+    for i in range(3):
+        ip, ix, ct = so.overlap_csr(labs[i], 16, 32, 60)
+        area, sy, sx = so.superpixel_stats(labs[i], 60)
+        of.append(so.pool_count(ip, ix, ct, feats[i].reshape(32, -1).T, area, sy, sx, True))
+        ow.append(so.create_prior(labs[i], 0.75, 0.5, 0.1, 0.1))
+    of, ow = np.concatenate(of), np.concatenate(ow)
+    np.testing.assert_allclose(f, of, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(w, ow, rtol=1e-12)
+    np.random.seed(1111)
+    oa = so.kmeans(4, f, w, verbose=False)        # same seeded stream, same X
+    ocm, orm = so.weighted_kmeans_paint(labs, oa, n_per)
+    assert np.array_equal(cres, ocm) and np.array_equal(road, orm)
+
+
+def test_kmeans_dropin_reference_golden_and_seed_parity(golden_dir):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    g = np.load(os.path.join(golden_dir, 'kmeans_ref.npz'))
+    for name in ('k4', 'k2', 'k8', 'k3_pos', 'nan_center'):
+        X, w, k = g[name + '__X'].astype(np.float64), g[name + '__w'], int(g[name + '__k'])
+        got = bsk.kmeans(k, X, w, init_assign=g[name + '__init'])
+        assert np.array_equal(np.asarray(got).astype(np.int32), g[name + '__assign']), name
+    # the golden vectors were produced by ONE seeded stream in this order: replaying the
+    # stream through the drop-in reproduces the reference without passing the init
+    np.random.seed(1111)
+    for name in ('k4', 'k2', 'k8', 'k3_pos'):
+        X, w, k = g[name + '__X'].astype(np.float64), g[name + '__w'], int(g[name + '__k'])
+        got = bsk.kmeans(k, X, w)
+        assert np.array_equal(np.asarray(got).astype(np.int32), g[name + '__assign']), name
+
+
+def test_kmeans_dropin_float64_rows_not_fp32_representable():
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    rs = np.random.RandomState(4)
+    X = np.concatenate([rs.standard_normal((80, 9)) + 4 * rs.standard_normal((1, 9)) for _ in range(4)])
+    w = rs.uniform(0, 1, len(X))
+    np.random.seed(5)
+    want = so.kmeans(4, X, w, verbose=False)
+    np.random.seed(5)
+    got = bsk.kmeans(4, X, w)
+    assert np.array_equal(np.asarray(want).astype(np.int32), np.asarray(got).astype(np.int32))
+
+
+def test_weighted_kmeans_dropin_reference_golden(golden_dir):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    g = np.load(os.path.join(golden_dir, 'weighted_kmeans_ref.npz'))
+    cres, road = bsk.weighted_kmeans(g['labs'], g['anchor_features'], g['weights'], int(g['k']),
+                                     list(g['n_per']), init_assign=g['init'])
+    assert cres.dtype == g['labs'].dtype
+    assert np.array_equal(cres, g['cluster_map']) and np.array_equal(road, g['road'])
+
+
+def test_prior_dropin_reference_golden(golden_dir):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    from superpixel_align_b200 import direct_clustering as dc
+    g = np.load(os.path.join(golden_dir, 'prior_ref.npz'))
+    bsk.clear_cache()
+    np.testing.assert_allclose(bsk.create_prior(g['lab_a'], 0.75, 0.5, 0.1, 0.1), g['w_a'], rtol=1e-12)
+    np.testing.assert_allclose(bsk.create_prior(g['lab_b'], 0.6, 0.4, 0.2, 0.15), g['w_b'], rtol=1e-12)
+    assert np.array_equal(dc.create_prior(28, 28, 0.75, 0.5, 0.1, 0.1), g['cell_28'])
+    assert np.array_equal(dc.create_prior(16, 32, 0.75, 0.5, 0.1, 0.1), g['cell_16x32'])
+
+
+def test_torch_carriers_stay_on_device(batch):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    labs, feats, imgs = batch
+    args = _args(without_pos=True)
+    d = torch.device('cuda', 0)
+    bsk.clear_cache()
+    lt = torch.from_numpy(labs.astype(np.int32)).to(d)
+    ft = torch.from_numpy(feats).to(d).contiguous(memory_format=torch.channels_last)
+    f, n_per = bsk.batch_superpixel_align(args, None, None, lt, ft)
+    w = bsk.batch_create_prior(args, lt)
+    assert f.is_cuda and w.is_cuda and f.shape == (180, 32)
+    np.random.seed(3)
+    cres, road = bsk.batch_weighted_kmeans(args, lt, f, w, n_per)
+    assert cres.is_cuda and cres.dtype == torch.int32 and road.dtype == torch.bool
+    np.random.seed(3)
+    oa = so.kmeans(4, f.cpu().numpy().astype(np.float64), w.cpu().numpy(), verbose=False)
+    ocm, _ = so.weighted_kmeans_paint(labs, oa, n_per)
+    assert np.array_equal(cres.cpu().numpy(), ocm.astype(np.int32))
+
+
+def test_direct_clustering_dropin(batch):
+    from superpixel_align_b200 import direct_clustering as dc
+    labs, feats, imgs = batch
+    args = _args()
+    X = so.direct_features(feats)
+    prior = so.create_prior_map(16, 32, 0.75, 0.5, 0.1, 0.1).reshape(1, -1).repeat(3, axis=0).reshape(-1)
+    np.random.seed(8)
+    want = so.kmeans(4, X, prior, verbose=False)
+    np.random.seed(8)
+    cres, road = dc.estimate_road_mask(feats, args)          # virtual (x, y) columns, no matrix
+    assert np.array_equal(cres.reshape(-1), np.asarray(want).astype(np.int32))
+    assert np.array_equal(road, cres == 0)
+    np.random.seed(8)
+    got2 = dc.batch_weighted_kmeans(args, X, prior)           # materialised matrix, as the reference
+    assert np.array_equal(np.asarray(got2).astype(np.int32), np.asarray(want).astype(np.int32))
+
+
+def test_superpixel_overlaps_dropin(batch):
+    from superpixel_align_b200 import superpixel_overlaps as spo
+    labs, feats, imgs = batch
+    args = _args(overlap_threshold=0.02)
+    np.random.seed(8)
+    refined, cres, road = spo.estimate_road_mask(feats, labs, args)
+    assert refined.shape == labs.shape and refined.dtype == np.uint8
+    for i in range(3):
+        want = so.refine_overlaps_masks(labs[i], so.upsample_nearest(road[i], 128, 256), 0.02)
+        assert np.array_equal(refined[i], want)
+
+
+def test_product_has_no_cpu_fallback():
+    from superpixel_align_b200 import _lib, ops
+    with pytest.raises(_lib.SpalignError):
+        ops.label_max(torch.zeros((1, 8, 8), dtype=torch.int32))   # CPU tensor
