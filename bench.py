@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""Benchmark of the superpixel-align hot path (BASELINE.json metric: images/sec at 1024x2048).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images M]
+
+One "step" = one pass of the hot path (K1 overlap CSR -> K2 pooling -> prior -> seeded init ->
+K3 per-image k-means -> K4 paint-back) over a batch of synthetic Cityscapes-shaped images that
+is already resident in HBM: BASELINE.json configs[1], 300 images of 1024x2048, SLIC-shaped
+~1000 superpixels, DRN-C-26 layer8 (stride 8, 512 channels) random-init features.  Under
+torchrun every rank owns its own range of a 300*N image set (the reference's shell rule,
+utils/create_val_labels.sh:38-52), no collective on the data path -> weak scaling.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
+reference path (oracle/, kind "port") on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FH, FW, C = 1024, 2048, 128, 256, 512
+GY, GX = 25, 40            # 1000 superpixels
+K = 4
+PRIOR = (0.75, 0.5, 0.1, 0.1)
+
+
+def shard_range(n_data, n_shards, rank):
+    """utils/create_val_labels.sh:38-52: step = n/N + 1; [i, min(i+step, n))."""
+    step = n_data // n_shards + 1
+    lo = min(rank * step, n_data)
+    return lo, min(lo + step, n_data)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                    'sw_power_cap'), f[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------- CPU baseline (port)
+def _cpu_one(job):
+    """One image through the oracle port of the count-matrix path (NumPy/SciPy, float64)."""
+    lab, feat_cell, seed = job
+    from oracle import spalign_oracle as so
+    rs = np.random.RandomState(seed)
+    t0 = time.time()
+    so.spalign_image_cpu(lab, feat_cell, FH, FW, k=K, prior=PRIOR, append_pos=True, rng=rs)
+    return time.time() - t0
+
+
+class CpuPort:
+    """Worker pool running the oracle port, one image per task."""
+
+    def __init__(self, labels, feats_cell, procs):
+        import multiprocessing as mp
+        self.labels, self.feats, self.procs = labels, feats_cell, procs
+        self.pool = mp.get_context('fork').Pool(procs)
+        self.run(procs)  # warm the workers (imports, page-in)
+
+    def run(self, n_images):
+        jobs = [(self.labels[i % len(self.labels)], self.feats[i % len(self.feats)], i)
+                for i in range(n_images)]
+        t0 = time.time()
+        per = self.pool.map(_cpu_one, jobs, chunksize=1)
+        dt = time.time() - t0
+        return n_images / dt, float(np.mean(per)), dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_port_throughput(labels, feats_cell, n_images, procs):
+    """images/s of the oracle port over `n_images` images with `procs` worker processes."""
+    port = CpuPort(labels, feats_cell, procs)
+    v, per, _ = port.run(n_images)
+    port.close()
+    return v, per
+
+
+def host_sample(n, use_cuda):
+    """`n` label maps + cell-major feature maps on the host (same generators as the GPU arm)."""
+    from superpixel_align_b200 import synth
+    labels = [synth.voronoi_labels(H, W, GY, GX, image_index=i) for i in range(n)]
+    feats = None
+    if use_cuda:
+        try:
+            import torch
+            from superpixel_align_b200 import drn
+            dev = torch.device('cuda', 0)
+            model = drn.drn_c_26(device=dev)
+            feats = []
+            for i in range(n):
+                img = synth.smooth_images_torch(1, H, W, first_index=i, device=dev)
+                f = synth.drn_features_torch(model, img)           # [1,512,128,256] channels_last
+                feats.append(f.permute(0, 2, 3, 1).reshape(FH * FW, C).cpu().numpy())
+            del model
+            torch.cuda.empty_cache()
+        except Exception as e:  # pragma: no cover
+            print('bench: DRN features unavailable (%s); using smooth noise' % e, file=sys.stderr)
+            feats = None
+    if feats is None:
+        feats = [synth.smooth_features(C, FH, FW, seed=i).reshape(C, -1).T.copy() for i in range(n)]
+    return labels, feats
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    n_pool = min(4, procs)
+    try:
+        import torch
+        use_cuda = torch.cuda.is_available()
+    except Exception:
+        use_cuda = False
+    labels, feats = host_sample(n_pool, use_cuda)
+    per_step = procs  # one image per worker per step: a bounded sample of the 300-image batch
+    port = CpuPort(labels, feats, procs)
+    for _ in range(args.warmup):
+        port.run(per_step)
+    dt, tot = 0.0, 0
+    for _ in range(args.steps):
+        dt += port.run(per_step)[2]
+        tot += per_step
+    port.close()
+    value = tot / dt
+    line = {
+        'impl': 'reference', 'metric': 'images/sec (1024x2048 hot path)', 'value': value,
+        'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1000.0 * dt / max(1, args.steps), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.images, int(os.environ.get('WORLD_SIZE', '1'))),
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': procs, 'kind': 'port',
+                         'sample': '%d images per step (one per worker process) of the 300-image '
+                                   'batch, oracle/spalign_oracle.py count-matrix path, float64' % per_step},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_images, n_gpus):
+    return {'workload': 'configs[1] random300-shaped batch: %d synthetic 1024x2048 images per GPU, '
+                        'SLIC-shaped 1000 superpixels (jittered Voronoi), DRN-C-26 layer8 512-ch '
+                        'stride-8 features (random init), per-image prior-weighted k-means K=4' % n_images,
+            'images_per_gpu': n_images, 'n_gpus': n_gpus, 'superpixels': GY * GX, 'channels': C,
+            'clustering': 'per-image (batchsize 1)', 'append_pos': True,
+            'l2_policy': 'inputs (%.1f GB per GPU) larger than the 126 MB L2; no flush needed'
+                         % (n_images * (FH * FW * C * 4 + H * W * 4) / 1e9),
+            'sharding': 'reference rule step = n/N + 1 over a 300*N image set, no collective'}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from superpixel_align_b200 import _lib, drn, ops, pipeline, synth
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    import types
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    lo, hi = shard_range(args.images * world, world, rank)
+    n_img = hi - lo
+    n_sp = [GY * GX] * n_img
+
+    # ---- inputs, resident in HBM ----
+    t_setup = time.time()
+    labels = synth.voronoi_labels_torch(n_img, H, W, GY, GX, first_index=lo, device=dev)
+    model = drn.drn_c_26(device=dev)
+    feats = torch.empty((n_img, FH * FW, C), dtype=torch.float32, device=dev)
+    bs = 2
+    for i in range(0, n_img, bs):
+        m = min(bs, n_img - i)
+        imgs = synth.smooth_images_torch(m, H, W, first_index=lo + i, device=dev)
+        f = synth.drn_features_torch(model, imgs)
+        feats[i:i + m] = f.permute(0, 2, 3, 1).reshape(m, FH * FW, C)
+    del model, imgs, f
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    def step(timers=None):
+        np.random.seed(1111)
+        return pipeline.run_batch(labels, feats, n_sp, FH, FW, k=K, prior=PRIOR, append_pos=True,
+                                  images_per_group=1, timers=timers)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    nnz = out.overlap.validate()
+    iters = out.iters.cpu().numpy()
+    status = out.status.cpu().numpy()
+    tie_groups = int((out.init_m.cpu().numpy() != out.shuf_sizes).sum())
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ev = []
+    ev0.record()
+    for _ in range(args.steps):
+        timers = {}
+        step(timers)
+        stage_ev.append(timers)
+    ev1.record()
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n_img)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    total_images = float(cnt.item())
+    value = total_images * args.steps / (ms_max / 1000.0)
+
+    stages = {}
+    for name in ('overlap', 'pool', 'init', 'kmeans', 'paint'):
+        v = [tm[name][0].elapsed_time(tm[name][1]) for tm in stage_ev if name in tm]
+        if v:
+            stages[name + '_ms'] = float(np.mean(v))
+
+    # ---- roofline of the dominant kernel (K2 pooling; K1 alongside) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    S = GY * GX
+    ld = ops.padded_ld(C + 2)
+    pool_bytes = n_img * (FH * FW * C * 4 + (S + 1) * 4 + S * (4 + 8 + 8) + S * ld * 4) + nnz * 8
+    k1_bytes = n_img * (H * W * 4 + (S + 1) * 4 + S * (4 + 8 + 8 + 8)) + nnz * 8
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('pool_rows_kernel')
+        if traffic is not None:
+            traffic = traffic * n_img  # stored per image
+    except Exception:
+        pass
+    roofline = None
+    if 'pool_ms' in stages:
+        ach = pool_bytes / (stages['pool_ms'] * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'pool_rows_kernel (K2 CSR SpMM pooling)',
+                    'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'peak_source': peak_src, 'traffic': traffic,
+                    'algorithmic_bytes_per_launch': pool_bytes,
+                    'launch_ms': stages['pool_ms']}
+        if 'overlap_ms' in stages:
+            k1 = k1_bytes / (stages['overlap_ms'] * 1e-3) / 1e9
+            roofline['k1_overlap'] = {'achieved': k1, 'frac': k1 / peak,
+                                      'algorithmic_bytes_per_launch': k1_bytes,
+                                      'launch_ms': stages['overlap_ms'], 'kernels': 7}
+            both = (pool_bytes + k1_bytes) / ((stages['pool_ms'] + stages['overlap_ms']) * 1e-3) / 1e9
+            roofline['k1_plus_k2'] = {'achieved': both, 'frac': both / peak,
+                                      'frac_of_nominal_8TBs': both / 8000.0}
+
+    # ---- end to end through the reference-facing drop-in API, host buffers ----
+    e2e = None
+    if rank == 0 or world > 1:
+        e2e = run_e2e(args, dev, labels, feats, world)
+
+    # ---- CPU baseline: oracle port on the host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        procs = max(1, min(cores, 32))
+        hl = [labels[i].cpu().numpy() for i in range(min(4, n_img))]
+        hf = [feats[i].cpu().numpy() for i in range(min(4, n_img))]
+        n_s = 2 * procs
+        v, per = cpu_port_throughput(hl, hf, n_s, procs)
+        cpu = {'value': v, 'unit': 'images/s', 'cores': procs, 'kind': 'port',
+               'sample': '%d of the 300 images, %d worker processes, oracle/spalign_oracle.py '
+                         '(NumPy/SciPy float64 count-matrix path), %.2f s per image per core'
+                         % (n_s, procs, per)}
+
+    if rank == 0:
+        line = {
+            'metric': 'images/sec (1024x2048 hot path)', 'value': value, 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 pooling / f64 k-means / i32 overlap',
+            'data': 'synthetic', 'config': workload_config(args.images, world),
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'stages_ms_per_step': stages,
+            'kmeans': {'iters_mean': float(iters.mean()), 'iters_max': int(iters.max()),
+                       'status_counts': {str(s): int((status == s).sum()) for s in np.unique(status)},
+                       'init_tie_groups': tie_groups},
+            'nnz_per_image': nnz / n_img, 'setup_s': t_setup,
+            'us_per_image': 1000.0 * ms_max / args.steps / n_img,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, dev, labels, feats, world):
+    """Same metric through the drop-in API (batch_superpixel_align -> batch_create_prior ->
+    batch_weighted_kmeans, batchsize 1 = per-image clustering) with inputs in pinned HOST
+    memory and the result masks copied back to the host, every step."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    n_img = labels.shape[0]
+    pool_n = min(args.host_pool, n_img)
+    h_lab = [labels[i:i + 1].cpu().pin_memory() for i in range(pool_n)]
+    # host features in channels_last [1, C, fh, fw] (cell-major bytes)
+    h_feat = [feats[i].reshape(1, FH, FW, C).permute(0, 3, 1, 2).cpu().pin_memory()
+              for i in range(pool_n)]
+    a = types.SimpleNamespace(gpu=dev.index, n_clusters=K, without_pos=False, y_rel_pos=PRIOR[0],
+                              x_rel_pos=PRIOR[1], y_rel_sigma=PRIOR[2], x_rel_sigma=PRIOR[3])
+    n_e2e = min(args.e2e_images, n_img)
+
+    def one(i):
+        lab, feat = h_lab[i % pool_n], h_feat[i % pool_n]
+        bsk.clear_cache()
+        lab_d = lab.to(dev, non_blocking=True)
+        f, n_per = bsk.batch_superpixel_align(a, None, None, lab_d,
+                                              feat.to(dev, non_blocking=True))
+        w = bsk.batch_create_prior(a, lab_d)
+        cres, road = bsk.batch_weighted_kmeans(a, lab_d, f, w, n_per)
+        return cres.to(torch.uint8).cpu(), road.cpu()
+
+    np.random.seed(1111)
+    for i in range(3):
+        c, r = one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        for i in range(n_e2e):
+            c, r = one(i)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    h2d = n_e2e * (H * W * 4 + FH * FW * C * 4)
+    d2h = n_e2e * (H * W + H * W)
+    return {'value': world * n_e2e * args.steps / dt, 'unit': 'images/s',
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'images_per_step': n_e2e,
+            'api': 'superpixel_align_b200.batch_spalign_kmeans.{batch_superpixel_align,'
+                   'batch_create_prior,batch_weighted_kmeans}, one image per call (batchsize 1), '
+                   'pinned host label map int32 + channels_last fp32 features in, uint8 cluster '
+                   'map + bool road mask out'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--images', type=int, default=300, help='images per GPU per step')
+    ap.add_argument('--e2e-images', type=int, default=60, help='images per e2e step')
+    ap.add_argument('--host-pool', type=int, default=8, help='distinct pinned host images')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

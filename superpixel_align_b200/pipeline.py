@@ -53,15 +53,32 @@ def draw_shuffles(k: int, group_sizes: Sequence[int]):
 def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence[int], fh: int,
               fw: int, k: int = 4, prior=(0.75, 0.5, 0.1, 0.1), append_pos: bool = True,
               images_per_group: int = 1, n_iter: int = 1000,
-              nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8) -> PipelineOutput:
+              nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8,
+              timers: Optional[dict] = None) -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
     1 = per-image clustering).  Groups of more than 4096 rows use the host-driven multi-CTA
     k-means (which polls a stop flag); everything else is sync-free."""
     n = labels.shape[0]
     n_sp = np.asarray(n_sp, dtype=np.int64)
+
+    def mark(name, first):
+        # optional CUDA-event brackets per stage (bench.py's roofline numbers)
+        if timers is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if first:
+            timers[name] = [ev, None]
+        else:
+            timers[name][1] = ev
+
+    mark('overlap', True)
     ov = ops.overlap_csr(labels, fh, fw, n_sp, prior=prior, nnz_cap_per_image=nnz_cap_per_image)
+    mark('overlap', False)
+    mark('pool', True)
     feats = ops.pool(feat_cellmajor, ov, append_pos=append_pos)
+    mark('pool', False)
     weights = ov.weights()
     g_idx = np.arange(0, n + 1, images_per_group)
     if g_idx[-1] != n:
@@ -73,9 +90,14 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
         flat, off, m_exp = draw_shuffles(k, sizes)
         goff = ov.sp_off if images_per_group == 1 else \
             torch.from_numpy(group_off_host).to(dev, non_blocking=True)
-        init, m = ops.kmeans_init_device(weights, goff, torch.from_numpy(flat).to(dev, non_blocking=True),
-                                         torch.from_numpy(off).to(dev, non_blocking=True))
+        flat_d = torch.from_numpy(flat).to(dev, non_blocking=True)
+        off_d = torch.from_numpy(off).to(dev, non_blocking=True)
+        mark('init', True)
+        init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
+        mark('init', False)
+        mark('kmeans', True)
         res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
+        mark('kmeans', False)
     else:
         # large joint groups: the median split needs a sort of N doubles -> host init
         w_host = weights.cpu().numpy()
@@ -92,8 +114,12 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
             m_list.append(int(low.sum()))
         m = torch.tensor(m_list, dtype=torch.int32)
         m_exp = np.asarray(m_list)
+        mark('kmeans', True)
         res = ops.KMeansLarge(feats, weights, torch.from_numpy(init_host).to(dev), k,
                               group_off_host, n_iter=n_iter).run()
+        mark('kmeans', False)
+    mark('paint', True)
     cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype)
+    mark('paint', False)
     return PipelineOutput(cmap, mask, res.assign, feats, weights, res.iters, res.status, m, ov,
                           group_off_host, m_exp)
