@@ -49,6 +49,12 @@ struct KmSmem {
   int* start;      // [KMAX+1]
   double* wsum;    // [KMAX]
   double* cnt;     // [KMAX]
+  double* red;     // [8][KMAX] block reduction scratch of the exact pass
+  float* cen32;    // [K][Dc] centres rounded to fp32 (screening pass)
+  float* cnorm;    // [KMAX] upper bound of ||c_k||
+  int* anew;       // [TR] new assignment per tile row (-1: undecided)
+  int* amb;        // [TR] tile rows that need the exact float64 pass
+  int* namb;       // [1]
   int* changed;    // [1]
 };
 
@@ -60,6 +66,8 @@ __host__ __device__ inline size_t km_smem_bytes(int TR, int srow, int K, int Dc)
   b += (size_t)TR * sizeof(double);
   b += (size_t)TR * sizeof(int);
   b += (KMAX + 1) * sizeof(int) + 2 * KMAX * sizeof(double) + 64;
+  b += (size_t)8 * KMAX * sizeof(double) + (size_t)K * Dc * sizeof(float) + KMAX * sizeof(float);
+  b += (size_t)2 * TR * sizeof(int) + 64;
   return b + 128;
 }
 
@@ -73,6 +81,12 @@ __device__ inline void km_carve(KmSmem& s, char* base, int TR, int srow, int K, 
   s.om = reinterpret_cast<double*>(base + o); o += (size_t)TR * sizeof(double);
   s.wsum = reinterpret_cast<double*>(base + o); o += KMAX * sizeof(double);
   s.cnt = reinterpret_cast<double*>(base + o); o += KMAX * sizeof(double);
+  s.red = reinterpret_cast<double*>(base + o); o += (size_t)8 * KMAX * sizeof(double);
+  s.cen32 = reinterpret_cast<float*>(base + o); o += (size_t)K * Dc * sizeof(float);
+  s.cnorm = reinterpret_cast<float*>(base + o); o += KMAX * sizeof(float);
+  s.anew = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
+  s.amb = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
+  s.namb = reinterpret_cast<int*>(base + o); o += 16;
   s.order = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
   s.start = reinterpret_cast<int*>(base + o); o += (KMAX + 1) * sizeof(int);
   s.changed = reinterpret_cast<int*>(base + o);
@@ -172,39 +186,180 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
     __syncthreads();
     const char* tile = s.buf[ti & 1];
 
-    // ---- phase 1: partial squared distances over this thread's column slice ----
     if (mode == 1) {
-      double dist[KMAX];
+      if (sizeof(XT) == 4) {
+        // ---- phase 1 (fp32 screening): partial squared distances over this thread's slice ----
+        float dist[KMAX];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) dist[k] = 0.0;
-      if (row < nvalid) {
-        const char* xr = tile + (size_t)row * a.srow;
-        for (int ch = ch0; ch < ch1; ++ch) {
-          double xv[VE];
-          load_chunk<XT, VE>(xr + (size_t)ch * 16, xv);
-          const int d = ch * VE;
-          const bool full = d + VE <= Dr;
+        for (int k = 0; k < KMAX; ++k) dist[k] = 0.f;
+        if (row < nvalid) {
+          const char* xr = tile + (size_t)row * a.srow;
+          for (int ch = ch0; ch < ch1; ++ch) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + (size_t)ch * 16);
+            const int d = ch * 4;
+            const bool full = d + 4 <= Dr;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
+              if (full) {
+                float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]);
+                df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]);
+                df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]);
+                df = xv.w - cv.w; dist[k] = fmaf(df, df, dist[k]);
+              } else {
+                if (d + 0 < Dr) { const float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]); }
+                if (d + 1 < Dr) { const float df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]); }
+                if (d + 2 < Dr) { const float df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]); }
+              }
+            }
+          }
+        }
+        float* partf = reinterpret_cast<float*>(s.part);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) partf[(size_t)t * KMAX + k] = dist[k];
+        __syncthreads();
+
+        // ---- combine A: fp32 argmin with a rigorous error bound; undecided rows -> exact ----
+        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u||c_k||)^2, u = 2^-24
+        // (centre rounding + subtraction rounding, then fp32 accumulation); constants below
+        // are 2x / 256u generous.  A row is decided only if every other cluster stays
+        // strictly farther after both bounds are applied.
+        if (t < 32) {
+          const int lane = t;
+          const bool valid = lane < nvalid && lane < TR;
+          bool undecided = false;
+          if (valid) {
+            float F[KMAX];
+            float px = 0.f, py = 0.f;
+            if (a.pos_mode) {
+              double dpx, dpy;
+              virtual_pos(a, trow0 + lane, &dpx, &dpy);
+              px = (float)dpx;
+              py = (float)dpy;
+            }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              float sum = 0.f;
+              for (int p = 0; p < NPART; ++p) sum += partf[(size_t)(p * TR + lane) * KMAX + k];
+              if (a.pos_mode) {
+                const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
+                const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
+                sum = fmaf(dx, dx, sum);
+                sum = fmaf(dy, dy, sum);
+              }
+              F[k] = sum;
+            }
+            int j = 0;
+            float best = F[0];
+#pragma unroll
+            for (int k = 1; k < KMAX; ++k) {
+              if (k >= K) break;
+              if (F[k] < best) { best = F[k]; j = k; }
+            }
+            const float c1 = 2.4e-7f, c2 = 1.6e-5f;
+            bool certain = true;
+            float lim = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              const float cn = c1 * s.cnorm[k];
+              const float B = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
+              if (k == j) lim = F[k] + B;
+            }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              const float cn = c1 * s.cnorm[k];
+              const float B = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
+              if (k != j) certain = certain && (F[k] - B > lim);
+            }
+            certain = certain && (lim == lim) && (lim < 3.0e38f);
+            s.anew[lane] = certain ? j : -1;
+            undecided = !certain;
+          }
+          const unsigned um = __ballot_sync(0xffffffffu, undecided);
+          if (undecided) s.amb[__popc(um & ((1u << lane) - 1u))] = lane;
+          if (lane == 0) *s.namb = __popc(um);
+        }
+        __syncthreads();
+
+        // ---- exact pass: float64 distances for the undecided rows, whole block per row ----
+        const int namb = *s.namb;
+        for (int ai = 0; ai < namb; ++ai) {
+          const int r = s.amb[ai];
+          const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)r * a.srow);
+          double p[KMAX];
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) p[k] = 0.0;
+          for (int d = t; d < Dr; d += KM_THREADS) {
+            const double xv = (double)xr[d];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              const double df = xv - s.cen[(size_t)k * a.Dc + d];
+              p[k] = fma(df, df, p[k]);
+            }
+          }
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
             if (k >= K) break;
-            const double* ck = s.cen + (size_t)k * a.Dc + d;
-            double cv[VE];
 #pragma unroll
-            for (int e = 0; e < VE; e += 2) {
-              const double2 c2 = *reinterpret_cast<const double2*>(ck + e);
-              cv[e] = c2.x;
-              cv[e + 1] = c2.y;
-            }
-            if (full) {
+            for (int o = 16; o > 0; o >>= 1) p[k] += __shfl_xor_sync(0xffffffffu, p[k], o);
+          }
+          if ((t & 31) == 0) {
 #pragma unroll
-              for (int e = 0; e < VE; ++e) {
-                const double df = xv[e] - cv[e];
-                dist[k] = fma(df, df, dist[k]);
+            for (int k = 0; k < KMAX; ++k) s.red[(size_t)(t >> 5) * KMAX + k] = p[k];
+          }
+          __syncthreads();
+          if (t == 0) {
+            double dd[KMAX];
+            double px = 0.0, py = 0.0;
+            if (a.pos_mode) virtual_pos(a, trow0 + r, &px, &py);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              double sum = 0.0;
+              for (int wq = 0; wq < KM_THREADS / 32; ++wq) sum += s.red[(size_t)wq * KMAX + k];
+              if (a.pos_mode) {
+                const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
+                const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
+                sum = fma(dx, dx, sum);
+                sum = fma(dy, dy, sum);
               }
-            } else {
+              dd[k] = sqrt(sum);
+            }
+            s.anew[r] = np_argmin(dd, K);
+          }
+          __syncthreads();
+        }
+      } else {
+        // ---- float64 rows: phase 1 entirely in float64 (no screening) ----
+        double dist[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) dist[k] = 0.0;
+        if (row < nvalid) {
+          const char* xr = tile + (size_t)row * a.srow;
+          for (int ch = ch0; ch < ch1; ++ch) {
+            double xv[VE];
+            load_chunk<XT, VE>(xr + (size_t)ch * 16, xv);
+            const int d = ch * VE;
+            const bool full = d + VE <= Dr;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k >= K) break;
+              const double* ck = s.cen + (size_t)k * a.Dc + d;
+              double cv[VE];
+#pragma unroll
+              for (int e = 0; e < VE; e += 2) {
+                const double2 c2 = *reinterpret_cast<const double2*>(ck + e);
+                cv[e] = c2.x;
+                cv[e + 1] = c2.y;
+              }
 #pragma unroll
               for (int e = 0; e < VE; ++e) {
-                if (d + e < Dr) {
+                if (full || d + e < Dr) {
                   const double df = xv[e] - cv[e];
                   dist[k] = fma(df, df, dist[k]);
                 }
@@ -212,13 +367,33 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
             }
           }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) s.part[(size_t)t * KMAX + k] = dist[k];
-      __syncthreads();
+        for (int k = 0; k < KMAX; ++k) s.part[(size_t)t * KMAX + k] = dist[k];
+        __syncthreads();
+        if (t < 32 && t < nvalid && t < TR) {
+          double d[KMAX];
+          double px = 0.0, py = 0.0;
+          if (a.pos_mode) virtual_pos(a, trow0 + t, &px, &py);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k >= K) break;
+            double sum = 0.0;
+            for (int p = 0; p < NPART; ++p) sum += s.part[(size_t)(p * TR + t) * KMAX + k];
+            if (a.pos_mode) {
+              const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
+              const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
+              sum = fma(dx, dx, sum);
+              sum = fma(dy, dy, sum);
+            }
+            d[k] = sqrt(sum);
+          }
+          s.anew[t] = np_argmin(d, K);
+        }
+        __syncthreads();
+      }
     }
 
-    // ---- combine: argmin, new assignment, omega, stable grouping by cluster ----
+    // ---- combine B: adopt the new assignment, omega, stable grouping by cluster ----
     if (t < 32) {
       const int lane = t;
       const bool valid = lane < nvalid && lane < TR;
@@ -229,23 +404,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
         const int64_t grow = trow0 + lane;
         const int a_old = assign[grow];
         if (mode == 1) {
-          double d[KMAX];
-          double px = 0.0, py = 0.0;
-          if (a.pos_mode) virtual_pos(a, grow, &px, &py);
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            if (k >= K) break;
-            double sum = 0.0;
-            for (int p = 0; p < NPART; ++p) sum += s.part[(size_t)(p * TR + lane) * KMAX + k];
-            if (a.pos_mode) {
-              const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
-              const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
-              sum = fma(dx, dx, sum);
-              sum = fma(dy, dy, sum);
-            }
-            d[k] = sqrt(sum);
-          }
-          a_new = np_argmin(d, K);
+          a_new = s.anew[lane];
           chg = a_new != a_old;
           assign[grow] = a_new;
           const double wv = a.w[grow];
@@ -352,6 +511,27 @@ __device__ __forceinline__ bool finalize_centers(const KmArgs& a, KmSmem& s, dou
   return empty;
 }
 
+// fp32 copies of the centres and ||c_k|| upper bounds for the screening pass
+__device__ __forceinline__ void prepare_screen(const KmArgs& a, KmSmem& s) {
+  const int t = threadIdx.x;
+  for (int i = t; i < a.K * a.Dc; i += KM_THREADS) {
+    const int d = i % a.Dc;
+    s.cen32[i] = d < a.D ? (float)s.cen[i] : 0.f;
+  }
+  const int wq = t >> 5, lane = t & 31;
+  if (wq < a.K) {
+    double sum = 0.0;
+    for (int d = lane; d < a.D; d += 32) {
+      const double c = s.cen[(size_t)wq * a.Dc + d];
+      sum = fma(c, c, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s.cnorm[wq] = (float)sqrt(sum) * 1.000001f;
+  }
+  __syncthreads();
+}
+
 template <typename XT, int TR>
 __global__ void __launch_bounds__(KM_THREADS, 1) kmeans_groups_kernel(GroupArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
@@ -378,6 +558,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) kmeans_groups_kernel(GroupArgs 
     ++it;
     zero_acc(acc);
     if (t == 0) *s.changed = 0;
+    if (sizeof(XT) == 4) prepare_screen(g.a, s);
     __syncthreads();
     km_sweep<XT, TR>(g.a, s, r0, r1, 1, g.assign, acc);
     const int changed = *s.changed;  // km_sweep ends with __syncthreads
@@ -435,6 +616,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) kmeans_sweep_kernel(SweepArgs g
   zero_acc(acc);
   if (t == 0) *s.changed = 0;
   __syncthreads();
+  if (g.mode == 1 && sizeof(XT) == 4) prepare_screen(g.a, s);
   km_sweep<XT, TR>(g.a, s, rb, re, g.mode, g.assign, acc);
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
