@@ -1,16 +1,23 @@
 // K3: prior-weighted k-means (replaces kmeans(), batch_spalign_kmeans.py:136-183).
 //
-// One "sweep" streams the rows of X through shared memory in tiles of TR rows
-// (cp.async, double buffered) and does, per tile:
-//   phase 1  distances: thread (row, part) accumulates sum_d (x-c_k)^2 in float64 over its
-//            slice of the columns for every cluster k; centres are read from shared memory
-//            as warp-wide broadcasts
-//   combine  warp 0: fixed-order sum of the column-slice partials, sqrt, NumPy-style argmin
-//            (first minimum, first NaN wins), new assignment, omega = w or 1-w, stable
-//            grouping of the tile's rows by cluster
-//   phase 2  centroid sums: thread t owns columns t, t+256, ... and adds omega*x for the
-//            tile's rows cluster by cluster, in row order -> every accumulator is a plain
-//            sequential float64 sum, bit-reproducible
+// One "sweep" streams the rows of X through shared memory in tiles of TR rows (cp.async,
+// double buffered) and does, per tile:
+//   phase 1   fp32 screening: thread (row, part) accumulates sum_d (x-c_k)^2 over its slice of
+//             the columns for every cluster k; centres (fp32 copies) are warp-wide broadcasts
+//   combine A warp 0: sums the slice partials, takes the fp32 argmin and proves it with a
+//             rigorous rounding-error bound; rows it cannot prove are listed as undecided
+//   exact     the whole block recomputes each undecided row in float64 (sqrt + NumPy argmin:
+//             first minimum, first NaN wins) -- exact ties and NaN centres land here
+//             (float64 inputs skip the screening and do phase 1 in float64)
+//   combine B warp 0: adopts the new assignment, omega = w or 1-w, stable grouping of the
+//             tile's rows by cluster; lane k keeps sum(omega), count and the virtual (x, y)
+//             column sums of cluster k, added in row order
+//   phase 2   centroid sums: thread t owns columns 2t, 2t+1 (+512, ...) and adds omega*x for the
+//             tile's rows cluster by cluster, in row order -> every accumulator is a plain
+//             sequential float64 sum, bit-reproducible
+// B200's FP64 pipe is ~1/8 of the FP32 rate, so float64 is kept to the places that decide the
+// result: the centroid sums and the undecided rows.
+//
 // Two drivers share the sweep: `kmeans_groups_kernel` (one persistent CTA per independent
 // problem, whole iteration loop on the device, no host sync) and `kmeans_sweep_kernel`
 // (one CTA per row chunk of a large problem; partials are summed in fixed chunk order by
@@ -22,7 +29,6 @@ namespace {
 
 constexpr int KM_THREADS = 256;
 constexpr int KMAX = 8;
-constexpr int NS = 8;  // column slots per thread -> D + 2 <= NS * KM_THREADS
 
 struct KmArgs {
   const void* X;
@@ -34,62 +40,68 @@ struct KmArgs {
   const double* w;
   int D;              // columns incl. virtual ones
   int Dr;             // stored columns
-  int Dc;             // centre row stride (doubles)
+  int Dc;             // centre row stride (elements)
   int K;
   int srow;           // shared-memory row stride in bytes
   int copy16;         // 16-byte chunks copied per row
+  int TR;             // rows per tile (power of two, <= 32)
+  int logTR;
 };
 
+// shared-memory carve-up (all offsets from the dynamic smem base)
 struct KmSmem {
-  char* buf[2];
-  double* cen;     // [K][Dc]
-  double* part;    // [KM_THREADS][KMAX]
-  double* om;      // [TR] omega by sorted position
-  int* order;      // [TR]
-  int* start;      // [KMAX+1]
-  double* wsum;    // [KMAX]
-  double* cnt;     // [KMAX]
-  double* red;     // [8][KMAX] block reduction scratch of the exact pass
-  float* cen32;    // [K][Dc] centres rounded to fp32 (screening pass)
-  float* cnorm;    // [KMAX] upper bound of ||c_k||
-  int* anew;       // [TR] new assignment per tile row (-1: undecided)
-  int* amb;        // [TR] tile rows that need the exact float64 pass
-  int* namb;       // [1]
-  int* changed;    // [1]
+  char* buf0;       // 2 tiles of TR*srow bytes
+  int tile_bytes;
+  double* cen;      // [K][Dc]
+  float* cen32;     // [K][Dc] centres rounded to fp32 (screening pass)
+  char* part;       // [KM_THREADS][KMAX] partial distances (float or double)
+  double* red;      // [8][KMAX] block reduction scratch of the exact pass
+  double* om;       // [TR] omega by sorted position
+  double* extra;    // [KMAX][4] sum(omega), count, sum(omega*px), sum(omega*py)
+  float* cnorm;     // [KMAX] upper bound of ||c_k||
+  int* order;       // [TR]
+  int* anew;        // [TR] new assignment per tile row (-1: undecided)
+  int* amb;         // [TR] tile rows that need the exact float64 pass
+  int* start;       // [KMAX+1]
+  int* namb;        // [1]
+  int* changed;     // [1]
 };
 
-__host__ __device__ inline size_t km_smem_bytes(int TR, int srow, int K, int Dc) {
-  size_t b = 0;
-  b += (size_t)2 * TR * srow + 32;
-  b += (size_t)K * Dc * sizeof(double);
-  b += (size_t)KM_THREADS * KMAX * sizeof(double);
-  b += (size_t)TR * sizeof(double);
-  b += (size_t)TR * sizeof(int);
-  b += (KMAX + 1) * sizeof(int) + 2 * KMAX * sizeof(double) + 64;
-  b += (size_t)8 * KMAX * sizeof(double) + (size_t)K * Dc * sizeof(float) + KMAX * sizeof(float);
-  b += (size_t)2 * TR * sizeof(int) + 64;
-  return b + 128;
-}
-
-__device__ inline void km_carve(KmSmem& s, char* base, int TR, int srow, int K, int Dc) {
+__host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
+                                           int Dc) {
   size_t o = 0;
-  s.buf[0] = base + o; o += (size_t)TR * srow;
-  s.buf[1] = base + o; o += (size_t)TR * srow + 32;
+  const size_t tile = (size_t)TR * srow;
+  if (s) { s->buf0 = base; s->tile_bytes = (int)tile; }
+  o += 2 * tile + 32;
   o = (o + 15) & ~(size_t)15;
-  s.cen = reinterpret_cast<double*>(base + o); o += (size_t)K * Dc * sizeof(double);
-  s.part = reinterpret_cast<double*>(base + o); o += (size_t)KM_THREADS * KMAX * sizeof(double);
-  s.om = reinterpret_cast<double*>(base + o); o += (size_t)TR * sizeof(double);
-  s.wsum = reinterpret_cast<double*>(base + o); o += KMAX * sizeof(double);
-  s.cnt = reinterpret_cast<double*>(base + o); o += KMAX * sizeof(double);
-  s.red = reinterpret_cast<double*>(base + o); o += (size_t)8 * KMAX * sizeof(double);
-  s.cen32 = reinterpret_cast<float*>(base + o); o += (size_t)K * Dc * sizeof(float);
-  s.cnorm = reinterpret_cast<float*>(base + o); o += KMAX * sizeof(float);
-  s.anew = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
-  s.amb = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
-  s.namb = reinterpret_cast<int*>(base + o); o += 16;
-  s.order = reinterpret_cast<int*>(base + o); o += (size_t)TR * sizeof(int);
-  s.start = reinterpret_cast<int*>(base + o); o += (KMAX + 1) * sizeof(int);
-  s.changed = reinterpret_cast<int*>(base + o);
+  if (s) s->cen = reinterpret_cast<double*>(base + o);
+  o += (size_t)K * Dc * sizeof(double);
+  if (s) s->cen32 = reinterpret_cast<float*>(base + o);
+  o += (size_t)K * Dc * sizeof(float);
+  o = (o + 15) & ~(size_t)15;
+  if (s) s->part = base + o;
+  o += (size_t)KM_THREADS * KMAX * sizeof(double);
+  if (s) s->red = reinterpret_cast<double*>(base + o);
+  o += (size_t)8 * KMAX * sizeof(double);
+  if (s) s->om = reinterpret_cast<double*>(base + o);
+  o += (size_t)32 * sizeof(double);
+  if (s) s->extra = reinterpret_cast<double*>(base + o);
+  o += (size_t)KMAX * 4 * sizeof(double);
+  if (s) s->cnorm = reinterpret_cast<float*>(base + o);
+  o += KMAX * sizeof(float);
+  if (s) s->order = reinterpret_cast<int*>(base + o);
+  o += 32 * sizeof(int);
+  if (s) s->anew = reinterpret_cast<int*>(base + o);
+  o += 32 * sizeof(int);
+  if (s) s->amb = reinterpret_cast<int*>(base + o);
+  o += 32 * sizeof(int);
+  if (s) s->start = reinterpret_cast<int*>(base + o);
+  o += (KMAX + 1) * sizeof(int);
+  if (s) s->namb = reinterpret_cast<int*>(base + o);
+  o += sizeof(int);
+  if (s) s->changed = reinterpret_cast<int*>(base + o);
+  o += sizeof(int);
+  return o + 64;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -115,19 +127,6 @@ __device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, int64_t r
   }
 }
 
-template <typename XT, int VE>
-__device__ __forceinline__ void load_chunk(const char* p, double* xv);
-template <>
-__device__ __forceinline__ void load_chunk<float, 4>(const char* p, double* xv) {
-  const float4 v = *reinterpret_cast<const float4*>(p);
-  xv[0] = (double)v.x; xv[1] = (double)v.y; xv[2] = (double)v.z; xv[3] = (double)v.w;
-}
-template <>
-__device__ __forceinline__ void load_chunk<double, 2>(const char* p, double* xv) {
-  const double2 v = *reinterpret_cast<const double2*>(p);
-  xv[0] = v.x; xv[1] = v.y;
-}
-
 // virtual position columns of global row n (direct_clustering.py:300-303): (x, y) cell index
 __device__ __forceinline__ void virtual_pos(const KmArgs& a, int64_t row, double* px, double* py) {
   const int64_t n = (a.pos_row0 + row) % a.pos_period;
@@ -136,47 +135,52 @@ __device__ __forceinline__ void virtual_pos(const KmArgs& a, int64_t row, double
 }
 
 // NumPy argmin over K doubles: first minimum; a NaN is minimal and the first NaN wins
-__device__ __forceinline__ int np_argmin(const double* d, int K) {
+template <int KT>
+__device__ __forceinline__ int np_argmin(const double (&d)[KT], int K) {
   double best = d[0];
   int idx = 0;
-  if (best != best) return 0;
+  bool done = best != best;
 #pragma unroll
-  for (int k = 1; k < KMAX; ++k) {
-    if (k >= K) break;
-    if (!(d[k] >= best)) {
+  for (int k = 1; k < KT; ++k) {
+    if (k < K && !done && !(d[k] >= best)) {
       best = d[k];
       idx = k;
-      if (best != best) break;
+      done = best != best;
     }
   }
   return idx;
 }
 
 // One pass over rows [row_begin, row_end).  mode 0: keep `assign`, omega = 1 (init means).
-// mode 1: reassign against s.cen, omega = w / 1-w.  acc[k][slot] accumulates column
-// slot*256+t of cluster k; columns D and D+1 are sum(omega) and the member count.
-template <typename XT, int TR>
-__device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row_begin, int64_t row_end, int mode,
-                         int32_t* __restrict__ assign, double (&acc)[KMAX][NS]) {
-  constexpr int NPART = KM_THREADS / TR;
+// mode 1: reassign against s.cen, omega = w / 1-w.  acc[k][sl][j] accumulates stored column
+// 2*(sl*256+t)+j of cluster k; s.extra[k] receives sum(omega), count and the virtual columns.
+template <typename XT, int KT, int NS2>
+__device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_t row_begin,
+                                         int64_t row_end, int mode, int32_t* __restrict__ assign,
+                                         double (&acc)[KT][NS2][2]) {
   constexpr int VE = 16 / (int)sizeof(XT);
+  constexpr bool kF32 = sizeof(XT) == 4;
   const int t = threadIdx.x;
-  const int K = a.K, Dr = a.Dr, D = a.D;
+  const int K = a.K, Dr = a.Dr, TR = a.TR;
+  const int NPART = KM_THREADS >> a.logTR;
   const int64_t N = row_end - row_begin;
   const int ntiles = (int)((N + TR - 1) / TR);
-  if (ntiles == 0) return;
-  const int row = t % TR, part = t / TR;
+  const int row = t & (TR - 1), part = t >> a.logTR;
   const int nch = (Dr + VE - 1) / VE;
   const int ch0 = (int)((long long)part * nch / NPART);
   const int ch1 = (int)((long long)(part + 1) * nch / NPART);
+  // lane k of warp 0: running sum(omega), count, sum(omega*px), sum(omega*py) of cluster k
+  double e_w = 0.0, e_n = 0.0, e_x = 0.0, e_y = 0.0;
 
-  issue_tile<XT>(a, s.buf[0], row_begin, (int)min((int64_t)TR, N));
-  cp_async_commit();
+  if (ntiles > 0) {
+    issue_tile<XT>(a, s.buf0, row_begin, (int)min((int64_t)TR, N));
+    cp_async_commit();
+  }
   for (int ti = 0; ti < ntiles; ++ti) {
     const int64_t trow0 = row_begin + (int64_t)ti * TR;
     const int nvalid = (int)min((int64_t)TR, row_end - trow0);
     if (ti + 1 < ntiles) {
-      issue_tile<XT>(a, s.buf[(ti + 1) & 1], trow0 + TR,
+      issue_tile<XT>(a, s.buf0 + (size_t)((ti + 1) & 1) * s.tile_bytes, trow0 + TR,
                      (int)min((int64_t)TR, row_end - (trow0 + TR)));
       cp_async_commit();
       cp_async_wait<1>();
@@ -184,53 +188,60 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
       cp_async_wait<0>();
     }
     __syncthreads();
-    const char* tile = s.buf[ti & 1];
+    const char* tile = s.buf0 + (size_t)(ti & 1) * s.tile_bytes;
 
     if (mode == 1) {
-      if (sizeof(XT) == 4) {
-        // ---- phase 1 (fp32 screening): partial squared distances over this thread's slice ----
-        float dist[KMAX];
+      if (kF32) {
+        // ---- phase 1 (fp32 screening) ----
+        float dist[KT];
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) dist[k] = 0.f;
+        for (int k = 0; k < KT; ++k) dist[k] = 0.f;
         if (row < nvalid) {
           const char* xr = tile + (size_t)row * a.srow;
           for (int ch = ch0; ch < ch1; ++ch) {
             const float4 xv = *reinterpret_cast<const float4*>(xr + (size_t)ch * 16);
             const int d = ch * 4;
-            const bool full = d + 4 <= Dr;
+            const float* cb = s.cen32 + d;
+            if (d + 4 <= Dr) {
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
-              const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
-              if (full) {
-                float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]);
-                df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]);
-                df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]);
-                df = xv.w - cv.w; dist[k] = fmaf(df, df, dist[k]);
-              } else {
-                if (d + 0 < Dr) { const float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]); }
-                if (d + 1 < Dr) { const float df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]); }
-                if (d + 2 < Dr) { const float df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]); }
+              for (int k = 0; k < KT; ++k) {
+                if (k < K) {
+                  const float4 cv = *reinterpret_cast<const float4*>(cb + (size_t)k * a.Dc);
+                  float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]);
+                  df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]);
+                  df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]);
+                  df = xv.w - cv.w; dist[k] = fmaf(df, df, dist[k]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < KT; ++k) {
+                if (k < K) {
+                  const float4 cv = *reinterpret_cast<const float4*>(cb + (size_t)k * a.Dc);
+                  if (d + 0 < Dr) { const float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]); }
+                  if (d + 1 < Dr) { const float df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]); }
+                  if (d + 2 < Dr) { const float df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]); }
+                }
               }
             }
           }
         }
         float* partf = reinterpret_cast<float*>(s.part);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) partf[(size_t)t * KMAX + k] = dist[k];
+        for (int k = 0; k < KT; ++k) partf[(size_t)t * KT + k] = dist[k];
         __syncthreads();
 
-        // ---- combine A: fp32 argmin with a rigorous error bound; undecided rows -> exact ----
-        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u||c_k||)^2, u = 2^-24
-        // (centre rounding + subtraction rounding, then fp32 accumulation); constants below
-        // are 2x / 256u generous.  A row is decided only if every other cluster stays
-        // strictly farther after both bounds are applied.
+        // ---- combine A: fp32 argmin proved by a rounding-error bound ----
+        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u*||c_k||)^2, u = 2^-24
+        // (centre rounding to fp32, subtraction rounding, fp32 accumulation).  The constants
+        // are generous (2^-22 and 256u).  A row is decided only when every other cluster
+        // stays strictly farther after both bounds are applied; NaN/inf never decide.
         if (t < 32) {
           const int lane = t;
           const bool valid = lane < nvalid && lane < TR;
           bool undecided = false;
           if (valid) {
-            float F[KMAX];
+            float F[KT];
             float px = 0.f, py = 0.f;
             if (a.pos_mode) {
               double dpx, dpy;
@@ -239,43 +250,37 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
               py = (float)dpy;
             }
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
+            for (int k = 0; k < KT; ++k) {
               float sum = 0.f;
-              for (int p = 0; p < NPART; ++p) sum += partf[(size_t)(p * TR + lane) * KMAX + k];
-              if (a.pos_mode) {
-                const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
-                const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
-                sum = fmaf(dx, dx, sum);
-                sum = fmaf(dy, dy, sum);
+              if (k < K) {
+                for (int p = 0; p < NPART; ++p) sum += partf[(size_t)(p * TR + lane) * KT + k];
+                if (a.pos_mode) {
+                  const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
+                  const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
+                  sum = fmaf(dx, dx, sum);
+                  sum = fmaf(dy, dy, sum);
+                }
               }
               F[k] = sum;
             }
             int j = 0;
             float best = F[0];
 #pragma unroll
-            for (int k = 1; k < KMAX; ++k) {
-              if (k >= K) break;
-              if (F[k] < best) { best = F[k]; j = k; }
-            }
+            for (int k = 1; k < KT; ++k)
+              if (k < K && F[k] < best) { best = F[k]; j = k; }
             const float c1 = 2.4e-7f, c2 = 1.6e-5f;
-            bool certain = true;
+            float B[KT];
             float lim = 0.f;
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
-              const float cn = c1 * s.cnorm[k];
-              const float B = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
-              if (k == j) lim = F[k] + B;
+            for (int k = 0; k < KT; ++k) {
+              const float cn = c1 * (k < K ? s.cnorm[k] : 0.f);
+              B[k] = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
+              if (k == j) lim = F[k] + B[k];
             }
+            bool certain = (lim == lim) && (lim < 3.0e38f);
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
-              const float cn = c1 * s.cnorm[k];
-              const float B = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
-              if (k != j) certain = certain && (F[k] - B > lim);
-            }
-            certain = certain && (lim == lim) && (lim < 3.0e38f);
+            for (int k = 0; k < KT; ++k)
+              if (k < K && k != j) certain = certain && (F[k] - B[k] > lim);
             s.anew[lane] = certain ? j : -1;
             undecided = !certain;
           }
@@ -290,104 +295,98 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
         for (int ai = 0; ai < namb; ++ai) {
           const int r = s.amb[ai];
           const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)r * a.srow);
-          double p[KMAX];
+          double p[KT];
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) p[k] = 0.0;
+          for (int k = 0; k < KT; ++k) p[k] = 0.0;
           for (int d = t; d < Dr; d += KM_THREADS) {
             const double xv = (double)xr[d];
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
-              const double df = xv - s.cen[(size_t)k * a.Dc + d];
-              p[k] = fma(df, df, p[k]);
+            for (int k = 0; k < KT; ++k) {
+              if (k < K) {
+                const double df = xv - s.cen[(size_t)k * a.Dc + d];
+                p[k] = fma(df, df, p[k]);
+              }
             }
           }
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            if (k >= K) break;
+          for (int k = 0; k < KT; ++k) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p[k] += __shfl_xor_sync(0xffffffffu, p[k], o);
           }
           if ((t & 31) == 0) {
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) s.red[(size_t)(t >> 5) * KMAX + k] = p[k];
+            for (int k = 0; k < KT; ++k) s.red[(size_t)(t >> 5) * KMAX + k] = p[k];
           }
           __syncthreads();
           if (t == 0) {
-            double dd[KMAX];
+            double dd[KT];
             double px = 0.0, py = 0.0;
             if (a.pos_mode) virtual_pos(a, trow0 + r, &px, &py);
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
+            for (int k = 0; k < KT; ++k) {
               double sum = 0.0;
-              for (int wq = 0; wq < KM_THREADS / 32; ++wq) sum += s.red[(size_t)wq * KMAX + k];
-              if (a.pos_mode) {
-                const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
-                const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
-                sum = fma(dx, dx, sum);
-                sum = fma(dy, dy, sum);
+              if (k < K) {
+                for (int wq = 0; wq < KM_THREADS / 32; ++wq) sum += s.red[(size_t)wq * KMAX + k];
+                if (a.pos_mode) {
+                  const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
+                  const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
+                  sum = fma(dx, dx, sum);
+                  sum = fma(dy, dy, sum);
+                }
               }
               dd[k] = sqrt(sum);
             }
-            s.anew[r] = np_argmin(dd, K);
+            s.anew[r] = np_argmin<KT>(dd, K);
           }
           __syncthreads();
         }
       } else {
         // ---- float64 rows: phase 1 entirely in float64 (no screening) ----
-        double dist[KMAX];
+        double dist[KT];
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) dist[k] = 0.0;
+        for (int k = 0; k < KT; ++k) dist[k] = 0.0;
         if (row < nvalid) {
           const char* xr = tile + (size_t)row * a.srow;
           for (int ch = ch0; ch < ch1; ++ch) {
-            double xv[VE];
-            load_chunk<XT, VE>(xr + (size_t)ch * 16, xv);
-            const int d = ch * VE;
-            const bool full = d + VE <= Dr;
+            const double2 xv = *reinterpret_cast<const double2*>(xr + (size_t)ch * 16);
+            const int d = ch * 2;
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (k >= K) break;
-              const double* ck = s.cen + (size_t)k * a.Dc + d;
-              double cv[VE];
-#pragma unroll
-              for (int e = 0; e < VE; e += 2) {
-                const double2 c2 = *reinterpret_cast<const double2*>(ck + e);
-                cv[e] = c2.x;
-                cv[e + 1] = c2.y;
-              }
-#pragma unroll
-              for (int e = 0; e < VE; ++e) {
-                if (full || d + e < Dr) {
-                  const double df = xv[e] - cv[e];
+            for (int k = 0; k < KT; ++k) {
+              if (k < K) {
+                const double2 cv = *reinterpret_cast<const double2*>(s.cen + (size_t)k * a.Dc + d);
+                double df = xv.x - cv.x;
+                dist[k] = fma(df, df, dist[k]);
+                if (d + 1 < Dr) {
+                  df = xv.y - cv.y;
                   dist[k] = fma(df, df, dist[k]);
                 }
               }
             }
           }
         }
+        double* partd = reinterpret_cast<double*>(s.part);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) s.part[(size_t)t * KMAX + k] = dist[k];
+        for (int k = 0; k < KT; ++k) partd[(size_t)t * KT + k] = dist[k];
         __syncthreads();
         if (t < 32 && t < nvalid && t < TR) {
-          double d[KMAX];
+          double dd[KT];
           double px = 0.0, py = 0.0;
           if (a.pos_mode) virtual_pos(a, trow0 + t, &px, &py);
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            if (k >= K) break;
+          for (int k = 0; k < KT; ++k) {
             double sum = 0.0;
-            for (int p = 0; p < NPART; ++p) sum += s.part[(size_t)(p * TR + t) * KMAX + k];
-            if (a.pos_mode) {
-              const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
-              const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
-              sum = fma(dx, dx, sum);
-              sum = fma(dy, dy, sum);
+            if (k < K) {
+              for (int p = 0; p < NPART; ++p) sum += partd[(size_t)(p * TR + t) * KT + k];
+              if (a.pos_mode) {
+                const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
+                const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
+                sum = fma(dx, dx, sum);
+                sum = fma(dy, dy, sum);
+              }
             }
-            d[k] = sqrt(sum);
+            dd[k] = sqrt(sum);
           }
-          s.anew[t] = np_argmin(d, K);
+          s.anew[t] = np_argmin<KT>(dd, K);
         }
         __syncthreads();
       }
@@ -417,12 +416,13 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
       int pos = 0, base = 0;
       const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k >= K) break;
-        const unsigned m = __ballot_sync(0xffffffffu, valid && a_new == k);
-        if (valid && a_new == k) pos = base + __popc(m & lt);
-        if (lane == 0) s.start[k] = base;
-        base += __popc(m);
+      for (int k = 0; k < KT; ++k) {
+        if (k < K) {
+          const unsigned m = __ballot_sync(0xffffffffu, valid && a_new == k);
+          if (valid && a_new == k) pos = base + __popc(m & lt);
+          if (lane == 0) s.start[k] = base;
+          base += __popc(m);
+        }
       }
       if (lane == 0) s.start[K] = base;
       if (valid && a_new >= 0 && a_new < K) {
@@ -431,88 +431,105 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, KmSmem& s, int64_t row
       }
       const unsigned cm = __ballot_sync(0xffffffffu, chg != 0);
       if (lane == 0 && cm) *s.changed += __popc(cm);
+      __syncwarp();
+      if (lane < K) {  // lane k: per-cluster scalars, rows in order
+        const int i1 = s.start[lane + 1];
+        for (int i = s.start[lane]; i < i1; ++i) {
+          const double o = s.om[i];
+          e_w += o;
+          e_n += 1.0;
+          if (a.pos_mode) {
+            double px, py;
+            virtual_pos(a, trow0 + s.order[i], &px, &py);
+            e_x = fma(o, px, e_x);
+            e_y = fma(o, py, e_y);
+          }
+        }
+      }
     }
     __syncthreads();
 
     // ---- phase 2: centroid sums, cluster by cluster, rows in order ----
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k >= K) break;
-      const int i1 = s.start[k + 1];
-      for (int i = s.start[k]; i < i1; ++i) {
-        const int r = s.order[i];
-        const double om = s.om[i];
-        const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)r * a.srow);
+    for (int k = 0; k < KT; ++k) {
+      if (k < K) {
+        const int i1 = s.start[k + 1];
+#pragma unroll 2
+        for (int i = s.start[k]; i < i1; ++i) {
+          const double om = s.om[i];
+          const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl) {
-          if (sl * KM_THREADS >= D + 2) break;
-          const int d = sl * KM_THREADS + t;
-          if (d < Dr) {
-            acc[k][sl] = fma(om, (double)xr[d], acc[k][sl]);
-          } else if (d < D) {  // virtual position columns
-            double px, py;
-            virtual_pos(a, trow0 + r, &px, &py);
-            acc[k][sl] = fma(om, (d == Dr) ? px : py, acc[k][sl]);
-          } else if (d == D) {
-            acc[k][sl] += om;
-          } else if (d == D + 1) {
-            acc[k][sl] += 1.0;
+          for (int sl = 0; sl < NS2; ++sl) {
+            const int c0 = 2 * (sl * KM_THREADS + t);
+            if (c0 + 1 < Dr) {
+              double x0, x1;
+              if (kF32) {
+                const float2 v = *reinterpret_cast<const float2*>(xr + c0);
+                x0 = (double)v.x;
+                x1 = (double)v.y;
+              } else {
+                const double2 v = *reinterpret_cast<const double2*>(xr + c0);
+                x0 = v.x;
+                x1 = v.y;
+              }
+              acc[k][sl][0] = fma(om, x0, acc[k][sl][0]);
+              acc[k][sl][1] = fma(om, x1, acc[k][sl][1]);
+            } else if (c0 < Dr) {
+              acc[k][sl][0] = fma(om, (double)xr[c0], acc[k][sl][0]);
+            }
           }
         }
       }
     }
     __syncthreads();
   }
-}
-
-__device__ __forceinline__ void zero_acc(double (&acc)[KMAX][NS]) {
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-#pragma unroll
-    for (int sl = 0; sl < NS; ++sl) acc[k][sl] = 0.0;
-}
-
-struct GroupArgs {
-  KmArgs a;
-  const int64_t* group_off;
-  int32_t* assign;
-  double* centers;  // may be null
-  int32_t* iters;
-  int32_t* status;
-  int n_iter;
-};
-
-// centres = sums / sum(omega); returns true when some cluster has no member
-__device__ __forceinline__ bool finalize_centers(const KmArgs& a, KmSmem& s, double (&acc)[KMAX][NS]) {
-  const int t = threadIdx.x;
-  const int D = a.D, K = a.K;
-#pragma unroll
-  for (int sl = 0; sl < NS; ++sl) {
-    const int d = sl * KM_THREADS + t;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (d == D) s.wsum[k] = acc[k][sl];
-      if (d == D + 1) s.cnt[k] = acc[k][sl];
-    }
+  if (t < K) {
+    s.extra[t * 4 + 0] = e_w;
+    s.extra[t * 4 + 1] = e_n;
+    s.extra[t * 4 + 2] = e_x;
+    s.extra[t * 4 + 3] = e_y;
   }
   __syncthreads();
+}
+
+template <int KT, int NS2>
+__device__ __forceinline__ void zero_acc(double (&acc)[KT][NS2][2]) {
 #pragma unroll
-  for (int sl = 0; sl < NS; ++sl) {
-    const int d = sl * KM_THREADS + t;
-    if (d < D) {
+  for (int k = 0; k < KT; ++k)
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) s.cen[(size_t)k * a.Dc + d] = acc[k][sl] / s.wsum[k];
+    for (int sl = 0; sl < NS2; ++sl) acc[k][sl][0] = acc[k][sl][1] = 0.0;
+}
+
+// centres = sums / sum(omega); returns true when some cluster has no member
+template <int KT, int NS2>
+__device__ __forceinline__ bool finalize_centers(const KmArgs& a, const KmSmem s,
+                                                 double (&acc)[KT][NS2][2]) {
+  const int t = threadIdx.x;
+  const int Dr = a.Dr, K = a.K;
+#pragma unroll
+  for (int sl = 0; sl < NS2; ++sl) {
+    const int c0 = 2 * (sl * KM_THREADS + t);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k < K) {
+        const double ws = s.extra[k * 4 + 0];
+        if (c0 < Dr) s.cen[(size_t)k * a.Dc + c0] = acc[k][sl][0] / ws;
+        if (c0 + 1 < Dr) s.cen[(size_t)k * a.Dc + c0 + 1] = acc[k][sl][1] / ws;
+      }
     }
   }
+  if (a.pos_mode && t < K) {
+    s.cen[(size_t)t * a.Dc + Dr] = s.extra[t * 4 + 2] / s.extra[t * 4 + 0];
+    s.cen[(size_t)t * a.Dc + Dr + 1] = s.extra[t * 4 + 3] / s.extra[t * 4 + 0];
+  }
   bool empty = false;
-  for (int k = 0; k < K; ++k) empty |= (s.cnt[k] == 0.0);
+  for (int k = 0; k < K; ++k) empty |= (s.extra[k * 4 + 1] == 0.0);
   __syncthreads();
   return empty;
 }
 
 // fp32 copies of the centres and ||c_k|| upper bounds for the screening pass
-__device__ __forceinline__ void prepare_screen(const KmArgs& a, KmSmem& s) {
+__device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) {
   const int t = threadIdx.x;
   for (int i = t; i < a.K * a.Dc; i += KM_THREADS) {
     const int d = i % a.Dc;
@@ -532,11 +549,21 @@ __device__ __forceinline__ void prepare_screen(const KmArgs& a, KmSmem& s) {
   __syncthreads();
 }
 
-template <typename XT, int TR>
-__global__ void __launch_bounds__(KM_THREADS, 1) kmeans_groups_kernel(GroupArgs g) {
+struct GroupArgs {
+  KmArgs a;
+  const int64_t* group_off;
+  int32_t* assign;
+  double* centers;  // may be null
+  int32_t* iters;
+  int32_t* status;
+  int n_iter;
+};
+
+template <typename XT, int KT, int NS2, int MINB>
+__global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(s, smem_raw, TR, g.a.srow, g.a.K, g.a.Dc);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc);
   const int grp = blockIdx.x;
   const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
   const int t = threadIdx.x;
@@ -547,26 +574,26 @@ __global__ void __launch_bounds__(KM_THREADS, 1) kmeans_groups_kernel(GroupArgs 
     }
     return;
   }
-  double acc[KMAX][NS];
-  zero_acc(acc);
+  double acc[KT][NS2][2];
+  zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   __syncthreads();
-  km_sweep<XT, TR>(g.a, s, r0, r1, 0, g.assign, acc);
-  finalize_centers(g.a, s, acc);
+  km_sweep<XT, KT, NS2>(g.a, s, r0, r1, 0, g.assign, acc);
+  finalize_centers<KT, NS2>(g.a, s, acc);
   int it = 0, status = SPALIGN_KM_ITER_CAP;
   while (it < g.n_iter) {
     ++it;
-    zero_acc(acc);
+    zero_acc<KT, NS2>(acc);
     if (t == 0) *s.changed = 0;
     if (sizeof(XT) == 4) prepare_screen(g.a, s);
     __syncthreads();
-    km_sweep<XT, TR>(g.a, s, r0, r1, 1, g.assign, acc);
+    km_sweep<XT, KT, NS2>(g.a, s, r0, r1, 1, g.assign, acc);
     const int changed = *s.changed;  // km_sweep ends with __syncthreads
     if (changed == 0) {
       status = SPALIGN_KM_CONVERGED;
       break;
     }
-    if (finalize_centers(g.a, s, acc)) {
+    if (finalize_centers<KT, NS2>(g.a, s, acc)) {
       status = SPALIGN_KM_EMPTY_CLUSTER;
       break;
     }
@@ -594,17 +621,17 @@ struct SweepArgs {
   double* partials;       // [n_chunks][K*(D+2)+1]
 };
 
-template <typename XT, int TR>
-__global__ void __launch_bounds__(KM_THREADS, 1) kmeans_sweep_kernel(SweepArgs g) {
+template <typename XT, int KT, int NS2, int MINB>
+__global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(s, smem_raw, TR, g.a.srow, g.a.K, g.a.Dc);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc);
   const int ck = blockIdx.x;
   const int grp = (int)g.chunks[(size_t)ck * 3];
   const int64_t rb = g.chunks[(size_t)ck * 3 + 1], re = g.chunks[(size_t)ck * 3 + 2];
   if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int t = threadIdx.x;
-  const int K = g.a.K, D = g.a.D;
+  const int K = g.a.K, D = g.a.D, Dr = g.a.Dr;
   if (g.mode == 1) {
     const double* c = g.centers + (size_t)grp * K * D;
     for (int i = t; i < K * D; i += KM_THREADS) {
@@ -612,22 +639,32 @@ __global__ void __launch_bounds__(KM_THREADS, 1) kmeans_sweep_kernel(SweepArgs g
       s.cen[(size_t)k * g.a.Dc + d] = c[i];
     }
   }
-  double acc[KMAX][NS];
-  zero_acc(acc);
+  double acc[KT][NS2][2];
+  zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   __syncthreads();
   if (g.mode == 1 && sizeof(XT) == 4) prepare_screen(g.a, s);
-  km_sweep<XT, TR>(g.a, s, rb, re, g.mode, g.assign, acc);
+  km_sweep<XT, KT, NS2>(g.a, s, rb, re, g.mode, g.assign, acc);
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
 #pragma unroll
-  for (int sl = 0; sl < NS; ++sl) {
-    const int d = sl * KM_THREADS + t;
-    if (d < D + 2) {
+  for (int sl = 0; sl < NS2; ++sl) {
+    const int c0 = 2 * (sl * KM_THREADS + t);
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) out[(size_t)k * (D + 2) + d] = acc[k][sl];
+    for (int k = 0; k < KT; ++k) {
+      if (k < K) {
+        if (c0 < Dr) out[(size_t)k * (D + 2) + c0] = acc[k][sl][0];
+        if (c0 + 1 < Dr) out[(size_t)k * (D + 2) + c0 + 1] = acc[k][sl][1];
+      }
     }
+  }
+  if (t < K) {
+    if (g.a.pos_mode) {
+      out[(size_t)t * (D + 2) + Dr] = s.extra[t * 4 + 2];
+      out[(size_t)t * (D + 2) + Dr + 1] = s.extra[t * 4 + 3];
+    }
+    out[(size_t)t * (D + 2) + D] = s.extra[t * 4 + 0];
+    out[(size_t)t * (D + 2) + D + 1] = s.extra[t * 4 + 1];
   }
   if (t == 0) out[pv - 1] = (double)*s.changed;
 }
@@ -747,7 +784,8 @@ kmeans_init_kernel(const double* __restrict__ w, const int64_t* __restrict__ gro
 
 // ------------------------------------------------------------------------------------------
 struct Plan {
-  int TR;
+  int variant;  // 0: <float,4,2> 2 CTAs/SM   1: <float,8,4>   2: <double,8,4>
+  int TR, logTR;
   int srow;
   int copy16;
   int Dc;
@@ -763,13 +801,19 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
   p->srow = srow;
   p->copy16 = row_bytes / 16;
   p->Dc = (int)align_up((size_t)D, 4);
-  const int trs[3] = {32, 16, 8};
-  for (int i = 0; i < 3; ++i) {
-    size_t b = km_smem_bytes(trs[i], srow, K, p->Dc);
-    if (b <= 200 * 1024) {
-      p->TR = trs[i];
-      p->smem = b;
-      return true;
+  const bool small = x_dtype == SPALIGN_F32 && K <= 4 && Dr <= 1024;
+  p->variant = x_dtype == SPALIGN_F64 ? 2 : (small ? 0 : 1);
+  // the small variant aims at two resident CTAs per SM (<= 110 KB each)
+  const size_t budgets[2] = {small ? (size_t)110 * 1024 : (size_t)200 * 1024, (size_t)200 * 1024};
+  for (int b = 0; b < 2; ++b) {
+    for (int tr = 32, lg = 5; tr >= 2; tr >>= 1, --lg) {
+      size_t bytes = km_carve(nullptr, nullptr, tr, srow, K, p->Dc);
+      if (bytes <= budgets[b] && (b == 1 || tr >= 8)) {
+        p->TR = tr;
+        p->logTR = lg;
+        p->smem = bytes;
+        return true;
+      }
     }
   }
   return false;
@@ -782,8 +826,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   SPALIGN_REQUIRE(K >= 2 && K <= KMAX, "kmeans: K must be in [2, %d]", KMAX);
   SPALIGN_REQUIRE(pos_mode == 0 || pos_mode == 1, "kmeans: bad pos_mode");
   const int Dr = D - (pos_mode ? 2 : 0);
-  SPALIGN_REQUIRE(Dr >= 1 && D + 2 <= NS * KM_THREADS, "kmeans: D out of range (max %d)",
-                  NS * KM_THREADS - 2);
+  SPALIGN_REQUIRE(Dr >= 1 && Dr <= 2048, "kmeans: stored columns out of range (max 2048)");
   const int es = x_dtype == SPALIGN_F32 ? 4 : 8;
   SPALIGN_REQUIRE((ldx * es) % 16 == 0 && ldx * es >= (int64_t)align_up((size_t)Dr * es, 16),
                   "kmeans: row stride must be a multiple of 16 bytes covering the padded row");
@@ -792,6 +835,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->X = X; a->ldx = ldx; a->pos_mode = pos_mode; a->pos_w = pos_w ? pos_w : 1;
   a->pos_period = pos_period ? pos_period : 1; a->pos_row0 = pos_row0; a->w = w;
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
+  a->TR = p.TR; a->logTR = p.logTR;
   return SPALIGN_OK;
 }
 
@@ -812,24 +856,18 @@ extern "C" size_t spalign_kmeans_groups_workspace_bytes(int D, int K, int G) {
   return 256;  // the persistent kernel keeps all state on chip
 }
 
-#define KM_DISPATCH(KERNEL, ARGS, GRID)                                                        \
-  do {                                                                                         \
-    int rc__ = SPALIGN_OK;                                                                     \
-    if (x_dtype == SPALIGN_F32) {                                                              \
-      if (plan.TR == 32) { rc__ = set_smem(KERNEL<float, 32>, plan.smem); if (rc__) return rc__; \
-        KERNEL<float, 32><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                     \
-      else if (plan.TR == 16) { rc__ = set_smem(KERNEL<float, 16>, plan.smem); if (rc__) return rc__; \
-        KERNEL<float, 16><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                     \
-      else { rc__ = set_smem(KERNEL<float, 8>, plan.smem); if (rc__) return rc__;              \
-        KERNEL<float, 8><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                      \
-    } else {                                                                                   \
-      if (plan.TR == 32) { rc__ = set_smem(KERNEL<double, 32>, plan.smem); if (rc__) return rc__; \
-        KERNEL<double, 32><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                    \
-      else if (plan.TR == 16) { rc__ = set_smem(KERNEL<double, 16>, plan.smem); if (rc__) return rc__; \
-        KERNEL<double, 16><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                    \
-      else { rc__ = set_smem(KERNEL<double, 8>, plan.smem); if (rc__) return rc__;             \
-        KERNEL<double, 8><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS); }                     \
-    }                                                                                          \
+#define KM_LAUNCH(KERNEL, XT, KT, NS2, MINB, ARGS, GRID)                                  \
+  do {                                                                                    \
+    int rc__ = set_smem(KERNEL<XT, KT, NS2, MINB>, plan.smem);                            \
+    if (rc__) return rc__;                                                                \
+    KERNEL<XT, KT, NS2, MINB><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS);             \
+  } while (0)
+
+#define KM_DISPATCH(KERNEL, ARGS, GRID)                                                   \
+  do {                                                                                    \
+    if (plan.variant == 0) KM_LAUNCH(KERNEL, float, 4, 2, 2, ARGS, GRID);                 \
+    else if (plan.variant == 1) KM_LAUNCH(KERNEL, float, 8, 4, 1, ARGS, GRID);            \
+    else KM_LAUNCH(KERNEL, double, 8, 4, 1, ARGS, GRID);                                  \
   } while (0)
 
 extern "C" int spalign_kmeans_groups(const void* X, int x_dtype, int64_t ldx, int pos_mode,

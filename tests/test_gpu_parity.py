@@ -444,3 +444,35 @@ def test_confusion_matches_oracle(ops):
     conf = ops.confusion2(torch.from_numpy(pred).to(dev()), torch.from_numpy(gt).to(dev())).cpu().numpy()
     for i in range(3):
         assert np.array_equal(conf[i], so.confusion(pred[i], gt[i], 2))
+
+
+def test_kmeans_exact_ties_and_near_ties_take_first_minimum(ops):
+    # rows exactly (or within 1e-7 relative) equidistant from two centres must go through the
+    # float64 fallback of the fp32 screening pass and follow NumPy's first-minimum rule
+    rs = np.random.RandomState(1)
+    D, K, N = 514, 4, 400
+    cen = rs.standard_normal((K, D)) * 3
+    cen[:, -2:] = rs.uniform(0, 2000, (K, 2))
+    cen = cen.astype(np.float32).astype(np.float64)
+    X = np.empty((N, D), dtype=np.float64)
+    for i in range(N):
+        a, b = rs.choice(K, 2, replace=False)
+        mid = 0.5 * (cen[a] + cen[b])
+        dirv = cen[b] - cen[a]
+        orth = rs.standard_normal(D)
+        orth -= orth.dot(dirv) / dirv.dot(dirv) * dirv
+        eps = [0.0, 1e-7, -1e-7, 1e-4, -1e-4][i % 5]
+        X[i] = mid + 0.01 * orth + eps * dirv
+    X = X.astype(np.float32)
+    w = rs.uniform(0, 1, N)
+    dist = np.linalg.norm(X.astype(np.float64)[:, None] - cen[None], axis=2)
+    want = dist.argmin(1).astype(np.int32)
+    for xd in (np.float32, np.float64):
+        km = ops.KMeansLarge(torch.from_numpy(X.astype(xd)).to(dev()), torch.from_numpy(w).to(dev()),
+                             torch.zeros(N, dtype=torch.int32, device=dev()), K, [0, N],
+                             chunks_per_group=2)
+        km.centers.copy_(torch.from_numpy(cen).to(dev())[None])
+        km._init_done = True
+        km.step()
+        assert np.array_equal(km.assign.cpu().numpy(), want)
+        assert km.iters[0].item() == 1
