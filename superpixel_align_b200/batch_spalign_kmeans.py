@@ -32,9 +32,6 @@ __all__ = ['create_prior', 'weighted_average', 'kmeans', 'weighted_kmeans', 'sup
            'batch_superpixel_align', 'batch_create_prior', 'batch_weighted_kmeans',
            'estimate_road_mask']
 
-# rows per group up to which the persistent single-CTA k-means is used
-GROUP_KERNEL_MAX_ROWS = 4096
-
 
 def _device(args=None):
     gpu = getattr(args, 'gpu', 0) if args is not None else 0
@@ -180,10 +177,8 @@ def _kmeans_device(k, X, w, init, n_iter, pos_grid=None, group_off_host=None):
     N = X.shape[0]
     if group_off_host is None:
         group_off_host = np.array([0, N], dtype=np.int64)
-    sizes = np.diff(group_off_host)
-    if sizes.max() <= GROUP_KERNEL_MAX_ROWS:
-        goff = torch.from_numpy(np.asarray(group_off_host, dtype=np.int64)).to(X.device)
-        return ops.kmeans_groups(X, w, init, k, goff, n_iter=n_iter, pos_grid=pos_grid)
+    # many CTAs per problem (ops.KMeansLarge): a lone 1000-row problem on one persistent CTA
+    # (ops.kmeans_groups) would leave 147 SMs idle
     return ops.KMeansLarge(X, w, init, k, group_off_host, n_iter=n_iter, pos_grid=pos_grid).run()
 
 

@@ -286,14 +286,18 @@ def kmeans_groups(X: torch.Tensor, w: torch.Tensor, init_assign: torch.Tensor, K
 
 
 class KMeansLarge:
-    """K3 for large groups: multi-CTA sweeps driven from the host, one step per iteration.
+    """K3 with many CTAs per problem: sweeps over row chunks driven from the host, one step per
+    iteration, for any number of independent groups at once.
 
-    ``step()`` enqueues sweep -> reduce -> [all-reduce hook] -> update.  ``run()`` loops and
-    polls the stop flags every ``poll`` iterations (one small D2H).  Used for joint batches,
-    direct cell clustering and (with ``allreduce``) the multi-GPU global clustering.
+    ``step()`` enqueues sweep -> reduce -> [all-reduce hook] -> update (3 launches).  ``run()``
+    loops, reads the stop flags every ``poll`` iterations (one small D2H) and re-cuts the chunk
+    list over the groups that are still running, so late iterations of a few slow groups still
+    spread over the whole GPU.  Used for batches of per-image problems, joint batches, direct
+    cell clustering and (with ``allreduce``) the multi-GPU global clustering.
     """
 
-    TILE = 32
+    TILE = 16           # rows per shared-memory tile of the main kernel variant
+    TARGET_CHUNKS = 4 * 148
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None):
@@ -308,29 +312,14 @@ class KMeansLarge:
         self.pos_period = pos_grid[0] * pos_grid[1] if pos_grid else 0
         self.pos_row0 = pos_row0
         self.allreduce = allreduce
-        dev = self.X.device
+        self.chunks_per_group = chunks_per_group
+        self.dev = dev = self.X.device
         self.w = w.to(torch.float64).contiguous()
         self.assign = init_assign.to(torch.int32).clone().contiguous()
-        goff = np.asarray(group_off_host, dtype=np.int64)
-        self.G = len(goff) - 1
-        chunks, gco = [], [0]
-        for g in range(self.G):
-            r0, r1 = int(goff[g]), int(goff[g + 1])
-            n = r1 - r0
-            tiles = max(1, math.ceil(n / self.TILE))
-            want = chunks_per_group or min(max(1, tiles // 4), max(1, (2 * 148) // self.G))
-            want = max(1, min(want, tiles))
-            per = math.ceil(tiles / want) * self.TILE
-            if n == 0:
-                chunks.append((g, r0, r0))
-            else:
-                for r in range(r0, r1, per):
-                    chunks.append((g, r, min(r + per, r1)))
-            gco.append(len(chunks))
-        self.n_chunks = len(chunks)
-        self.chunks = torch.tensor(chunks, dtype=torch.int64, device=dev).reshape(-1, 3)
-        self.gco = torch.tensor(gco, dtype=torch.int32, device=dev)
+        self.goff = np.asarray(group_off_host, dtype=np.int64)
+        self.G = len(self.goff) - 1
         self.pv = K * (self.D + 2) + 1
+        self._set_chunks(np.arange(self.G))
         self.partials = torch.zeros((self.n_chunks, self.pv), dtype=torch.float64, device=dev)
         self.totals = torch.zeros((self.G, self.pv), dtype=torch.float64, device=dev)
         self.centers = torch.zeros((self.G, K, self.D), dtype=torch.float64, device=dev)
@@ -339,7 +328,38 @@ class KMeansLarge:
         self._lib = _lib.load()
         self._init_done = False
 
+    def _set_chunks(self, active):
+        """Cut the rows of the ``active`` groups into chunks (vectorised; host side)."""
+        active = np.asarray(active, dtype=np.int64)
+        r0, r1 = self.goff[active], self.goff[active + 1]
+        n = r1 - r0
+        if self.chunks_per_group:
+            per = np.maximum(1, -(-n // self.chunks_per_group))
+            per = -(-per // self.TILE) * self.TILE
+        else:
+            total = int(n.sum())
+            rpc = max(2 * self.TILE, min(16 * self.TILE, total // self.TARGET_CHUNKS))
+            rpc = -(-rpc // self.TILE) * self.TILE
+            per = np.full(len(active), rpc, dtype=np.int64)
+        nch = np.maximum(1, -(-n // per))
+        tot = int(nch.sum())
+        rep = np.repeat(np.arange(len(active)), nch)
+        j = np.arange(tot) - np.repeat(np.cumsum(nch) - nch, nch)
+        rb = r0[rep] + j * per[rep]
+        re = np.minimum(rb + per[rep], r1[rep])
+        chunks = np.stack([active[rep], rb, np.maximum(re, rb)], axis=1).astype(np.int64)
+        counts = np.zeros(self.G, dtype=np.int64)
+        counts[active] = nch
+        gco = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.n_chunks = tot
+        if getattr(self, 'partials', None) is not None and tot > self.partials.shape[0]:
+            self.partials = torch.zeros((tot, self.pv), dtype=torch.float64, device=self.dev)
+        self.chunks = torch.from_numpy(chunks).to(self.dev, non_blocking=True)
+        self.gco = torch.from_numpy(gco).to(self.dev, non_blocking=True)
+
     def _sweep(self, mode):
+        if self.n_chunks == 0:
+            return
         check(self._lib.spalign_kmeans_sweep(
             _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
             self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
@@ -366,17 +386,22 @@ class KMeansLarge:
             self.init_centers()
         self._sweep(1)
 
-    def run(self, poll: int = 4) -> KMeansResult:
-        """Synchronises every ``poll`` iterations to read the stop flags."""
+    def run(self, poll: int = 4, first_poll: int = 6) -> KMeansResult:
+        """Synchronises at the poll points (after ``first_poll`` iterations, then every
+        ``poll``) to read the stop flags and drop finished groups from the chunk list."""
         if not self._init_done:
             self.init_centers()
-        done = 0
+        done, nxt = 0, min(first_poll, self.n_iter) if self.n_iter else 0
         while done < self.n_iter:
-            for _ in range(min(poll, self.n_iter - done)):
+            while done < nxt:
                 self._sweep(1)
-            done += poll
-            if bool((self.status != _lib.KM_RUNNING).all().item()):
+                done += 1
+            running = (self.status == _lib.KM_RUNNING).cpu().numpy()   # sync
+            if not running.any():
                 break
+            if self.allreduce is None and self.chunks_per_group is None:
+                self._set_chunks(np.nonzero(running)[0])
+            nxt = min(done + poll, self.n_iter)
         if self.n_iter == 0:
             self.status.fill_(_lib.KM_ITER_CAP)
         return KMeansResult(self.assign, self.iters, self.status, self.centers)

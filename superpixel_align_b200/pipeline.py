@@ -54,7 +54,7 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
               fw: int, k: int = 4, prior=(0.75, 0.5, 0.1, 0.1), append_pos: bool = True,
               images_per_group: int = 1, n_iter: int = 1000,
               nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8,
-              timers: Optional[dict] = None) -> PipelineOutput:
+              timers: Optional[dict] = None, kmeans_impl: str = 'chunks') -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
     1 = per-image clustering).  Groups of more than 4096 rows use the host-driven multi-CTA
@@ -96,7 +96,10 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
         init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
         mark('init', False)
         mark('kmeans', True)
-        res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
+        if kmeans_impl == 'groups':
+            res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
+        else:  # many CTAs per image, finished images dropped as the iterations go on
+            res = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter).run()
         mark('kmeans', False)
     else:
         # large joint groups: the median split needs a sort of N doubles -> host init
