@@ -22,6 +22,8 @@
 // problem, whole iteration loop on the device, no host sync) and `kmeans_sweep_kernel`
 // (one CTA per row chunk of a large problem; partials are summed in fixed chunk order by
 // `kmeans_reduce_kernel`, optionally all-reduced across GPUs, then `kmeans_update_kernel`).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace spalign {
@@ -80,7 +82,7 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += (size_t)K * Dc * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   if (s) s->part = base + o;
-  o += (size_t)KM_THREADS * KMAX * sizeof(double);
+  o += (size_t)KM_THREADS * KMAX * sizeof(double) + 8 * 32 * 33 * sizeof(float);
   if (s) s->red = reinterpret_cast<double*>(base + o);
   o += (size_t)8 * KMAX * sizeof(double);
   if (s) s->om = reinterpret_cast<double*>(base + o);
@@ -154,7 +156,7 @@ __device__ __forceinline__ int np_argmin(const double (&d)[KT], int K) {
 // One pass over rows [row_begin, row_end).  mode 0: keep `assign`, omega = 1 (init means).
 // mode 1: reassign against s.cen, omega = w / 1-w.  acc[k][sl][j] accumulates stored column
 // 2*(sl*256+t)+j of cluster k; s.extra[k] receives sum(omega), count and the virtual columns.
-template <typename XT, int KT, int NS2>
+template <typename XT, int KT, int NS2, int R>
 __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_t row_begin,
                                          int64_t row_end, int mode, int32_t* __restrict__ assign,
                                          double (&acc)[KT][NS2][2]) {
@@ -187,106 +189,121 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     } else {
       cp_async_wait<0>();
     }
+    if (t == 0) *s.namb = 0;
     __syncthreads();
     const char* tile = s.buf0 + (size_t)(ti & 1) * s.tile_bytes;
 
     if (mode == 1) {
       if (kF32) {
-        // ---- phase 1 (fp32 screening) ----
-        float dist[KT];
+        // ---- phase 1 (fp32 screening): one warp owns R rows, lanes stride the columns ----
+        constexpr int NV = R * KT;      // partial sums per lane
+        constexpr int LPV = 32 / NV;    // lanes that share the final sum of one value
+        static_assert(NV <= 32 && 32 % NV == 0, "R*KT must divide 32");
+        const int lane = t & 31, wq = t >> 5;
+        const int rbase = wq * R;
+        float a1[R][KT];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) dist[k] = 0.f;
-        if (row < nvalid) {
-          const char* xr = tile + (size_t)row * a.srow;
-          for (int ch = ch0; ch < ch1; ++ch) {
-            const float4 xv = *reinterpret_cast<const float4*>(xr + (size_t)ch * 16);
-            const int d = ch * 4;
-            const float* cb = s.cen32 + d;
-            if (d + 4 <= Dr) {
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-              for (int k = 0; k < KT; ++k) {
-                if (k < K) {
-                  const float4 cv = *reinterpret_cast<const float4*>(cb + (size_t)k * a.Dc);
-                  float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]);
-                  df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]);
-                  df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]);
-                  df = xv.w - cv.w; dist[k] = fmaf(df, df, dist[k]);
-                }
-              }
-            } else {
+          for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
+        const int main_d = Dr & ~127;
+        const char* xw = tile + (size_t)rbase * a.srow;
+        for (int d = lane * 4; d < main_d; d += 128) {
+          float4 xv[R];
 #pragma unroll
-              for (int k = 0; k < KT; ++k) {
-                if (k < K) {
-                  const float4 cv = *reinterpret_cast<const float4*>(cb + (size_t)k * a.Dc);
-                  if (d + 0 < Dr) { const float df = xv.x - cv.x; dist[k] = fmaf(df, df, dist[k]); }
-                  if (d + 1 < Dr) { const float df = xv.y - cv.y; dist[k] = fmaf(df, df, dist[k]); }
-                  if (d + 2 < Dr) { const float df = xv.z - cv.z; dist[k] = fmaf(df, df, dist[k]); }
-                }
+          for (int r = 0; r < R; ++r)
+            xv[r] = *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            if (k < K) {
+              const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                float df = xv[r].x - cv.x; a1[r][k] = fmaf(df, df, a1[r][k]);
+                df = xv[r].y - cv.y; a1[r][k] = fmaf(df, df, a1[r][k]);
+                df = xv[r].z - cv.z; a1[r][k] = fmaf(df, df, a1[r][k]);
+                df = xv[r].w - cv.w; a1[r][k] = fmaf(df, df, a1[r][k]);
               }
             }
           }
         }
-        float* partf = reinterpret_cast<float*>(s.part);
+        for (int d = main_d + lane; d < Dr; d += 32) {  // columns past the last multiple of 128
+          float xs[R];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) partf[(size_t)t * KT + k] = dist[k];
-        __syncthreads();
-
-        // ---- combine A: fp32 argmin proved by a rounding-error bound ----
-        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u*||c_k||)^2, u = 2^-24
-        // (centre rounding to fp32, subtraction rounding, fp32 accumulation).  The constants
-        // are generous (2^-22 and 256u).  A row is decided only when every other cluster
-        // stays strictly farther after both bounds are applied; NaN/inf never decide.
-        if (t < 32) {
-          const int lane = t;
-          const bool valid = lane < nvalid && lane < TR;
-          bool undecided = false;
-          if (valid) {
-            float F[KT];
-            float px = 0.f, py = 0.f;
-            if (a.pos_mode) {
-              double dpx, dpy;
-              virtual_pos(a, trow0 + lane, &dpx, &dpy);
-              px = (float)dpx;
-              py = (float)dpy;
-            }
+          for (int r = 0; r < R; ++r)
+            xs[r] = reinterpret_cast<const float*>(xw + (size_t)r * a.srow)[d];
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              float sum = 0.f;
-              if (k < K) {
-                for (int p = 0; p < NPART; ++p) sum += partf[(size_t)(p * TR + lane) * KT + k];
-                if (a.pos_mode) {
-                  const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
-                  const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
-                  sum = fmaf(dx, dx, sum);
-                  sum = fmaf(dy, dy, sum);
-                }
+          for (int k = 0; k < KT; ++k) {
+            if (k < K) {
+              const float c = s.cen32[(size_t)k * a.Dc + d];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const float df = xs[r] - c;
+                a1[r][k] = fmaf(df, df, a1[r][k]);
               }
-              F[k] = sum;
             }
-            int j = 0;
-            float best = F[0];
+          }
+        }
+        // warp-level sum of the NV values through a padded shared-memory transpose (fixed order)
+        float* pw = reinterpret_cast<float*>(s.part) + (size_t)wq * (NV * 33);
 #pragma unroll
-            for (int k = 1; k < KT; ++k)
-              if (k < K && F[k] < best) { best = F[k]; j = k; }
-            const float c1 = 2.4e-7f, c2 = 1.6e-5f;
-            float B[KT];
-            float lim = 0.f;
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) pw[(r * KT + k) * 33 + lane] = a1[r][k];
+        __syncwarp();
+        float tot = 0.f;
+        {
+          const int v = lane % NV, seg = lane / NV;
+          const float* src = pw + v * 33 + seg * (32 / LPV);
+#pragma unroll
+          for (int j = 0; j < 32 / LPV; ++j) tot += src[j];
+#pragma unroll
+          for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        }
+        // lane r (< R) finishes row rbase + r: fp32 argmin proved by a rounding-error bound.
+        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u*||c_k||)^2, u = 2^-24
+        // (centre rounding to fp32, subtraction rounding, fp32 accumulation); the constants are
+        // generous (2^-22 and 256u).  A row is decided only when every other cluster stays
+        // strictly farther after both bounds are applied; NaN/inf never decide.
+        float F[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) F[k] = __shfl_sync(0xffffffffu, tot, (lane % R) * KT + k);
+        if (lane < R && rbase + lane < nvalid) {
+          const int rr = rbase + lane;
+          if (a.pos_mode) {
+            double dpx, dpy;
+            virtual_pos(a, trow0 + rr, &dpx, &dpy);
+            const float px = (float)dpx, py = (float)dpy;
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
-              const float cn = c1 * (k < K ? s.cnorm[k] : 0.f);
-              B[k] = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
-              if (k == j) lim = F[k] + B[k];
+              if (k < K) {
+                const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
+                const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
+                F[k] = fmaf(dx, dx, F[k]);
+                F[k] = fmaf(dy, dy, F[k]);
+              }
             }
-            bool certain = (lim == lim) && (lim < 3.0e38f);
-#pragma unroll
-            for (int k = 0; k < KT; ++k)
-              if (k < K && k != j) certain = certain && (F[k] - B[k] > lim);
-            s.anew[lane] = certain ? j : -1;
-            undecided = !certain;
           }
-          const unsigned um = __ballot_sync(0xffffffffu, undecided);
-          if (undecided) s.amb[__popc(um & ((1u << lane) - 1u))] = lane;
-          if (lane == 0) *s.namb = __popc(um);
+          int j = 0;
+          float best = F[0];
+#pragma unroll
+          for (int k = 1; k < KT; ++k)
+            if (k < K && F[k] < best) { best = F[k]; j = k; }
+          const float c1 = 2.4e-7f, c2 = 1.6e-5f;
+          float B[KT];
+          float lim = 0.f;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            const float cn = c1 * (k < K ? s.cnorm[k] : 0.f);
+            B[k] = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
+            if (k == j) lim = F[k] + B[k];
+          }
+          bool certain = (lim == lim) && (lim < 3.0e38f);
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (k < K && k != j) certain = certain && (F[k] - B[k] > lim);
+          s.anew[rr] = certain ? j : -1;
+          if (!certain) s.amb[atomicAdd(s.namb, 1)] = rr;
         }
         __syncthreads();
 
@@ -559,7 +576,7 @@ struct GroupArgs {
   int n_iter;
 };
 
-template <typename XT, int KT, int NS2, int MINB>
+template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   __syncthreads();
-  km_sweep<XT, KT, NS2>(g.a, s, r0, r1, 0, g.assign, acc);
+  km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 0, g.assign, acc);
   finalize_centers<KT, NS2>(g.a, s, acc);
   int it = 0, status = SPALIGN_KM_ITER_CAP;
   while (it < g.n_iter) {
@@ -587,7 +604,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
     if (t == 0) *s.changed = 0;
     if (sizeof(XT) == 4) prepare_screen(g.a, s);
     __syncthreads();
-    km_sweep<XT, KT, NS2>(g.a, s, r0, r1, 1, g.assign, acc);
+    km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 1, g.assign, acc);
     const int changed = *s.changed;  // km_sweep ends with __syncthreads
     if (changed == 0) {
       status = SPALIGN_KM_CONVERGED;
@@ -621,7 +638,7 @@ struct SweepArgs {
   double* partials;       // [n_chunks][K*(D+2)+1]
 };
 
-template <typename XT, int KT, int NS2, int MINB>
+template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   if (t == 0) *s.changed = 0;
   __syncthreads();
   if (g.mode == 1 && sizeof(XT) == 4) prepare_screen(g.a, s);
-  km_sweep<XT, KT, NS2>(g.a, s, rb, re, g.mode, g.assign, acc);
+  km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc);
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
 #pragma unroll
@@ -784,7 +801,8 @@ kmeans_init_kernel(const double* __restrict__ w, const int64_t* __restrict__ gro
 
 // ------------------------------------------------------------------------------------------
 struct Plan {
-  int variant;  // 0: <float,4,2> 2 CTAs/SM   1: <float,8,4>   2: <double,8,4>
+  int variant;  // 0: <float,K<=4,Dr<=1024>   1: <float,K<=8,Dr<=2048>   2: <double,K<=8,Dr<=2048>
+  int R;        // rows per warp in the fp32 screening pass (TR = 8*R); double path: TR free
   int TR, logTR;
   int srow;
   int copy16;
@@ -803,17 +821,33 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
   p->Dc = (int)align_up((size_t)D, 4);
   const bool small = x_dtype == SPALIGN_F32 && K <= 4 && Dr <= 1024;
   p->variant = x_dtype == SPALIGN_F64 ? 2 : (small ? 0 : 1);
-  // the small variant aims at two resident CTAs per SM (<= 110 KB each)
-  const size_t budgets[2] = {small ? (size_t)110 * 1024 : (size_t)200 * 1024, (size_t)200 * 1024};
-  for (int b = 0; b < 2; ++b) {
+  const size_t limit = (size_t)200 * 1024;
+  if (p->variant == 2) {
     for (int tr = 32, lg = 5; tr >= 2; tr >>= 1, --lg) {
       size_t bytes = km_carve(nullptr, nullptr, tr, srow, K, p->Dc);
-      if (bytes <= budgets[b] && (b == 1 || tr >= 8)) {
-        p->TR = tr;
-        p->logTR = lg;
-        p->smem = bytes;
+      if (bytes <= limit) {
+        p->TR = tr; p->logTR = lg; p->R = 1; p->smem = bytes;
         return true;
       }
+    }
+    return false;
+  }
+  // fp32: TR = 8*R.  Variant 0 prefers R=2 (two CTAs per SM, fp32 and fp64 phases of the two
+  // CTAs overlap) unless SPALIGN_KM_R=4 asks for the bigger tile; variant 1 takes R=2 then 1.
+  int want = small ? 2 : 2;
+  if (const char* e = getenv("SPALIGN_KM_R")) {
+    int v = atoi(e);
+    if (small && (v == 2 || v == 4)) want = v;
+  }
+  const int cands[3] = {want, 2, 1};
+  for (int i = 0; i < 3; ++i) {
+    int r = cands[i];
+    if (!small && r == 4) continue;
+    if (small && r == 1) continue;
+    size_t bytes = km_carve(nullptr, nullptr, 8 * r, srow, K, p->Dc);
+    if (bytes <= limit) {
+      p->R = r; p->TR = 8 * r; p->logTR = r == 4 ? 5 : (r == 2 ? 4 : 3); p->smem = bytes;
+      return true;
     }
   }
   return false;
@@ -856,18 +890,20 @@ extern "C" size_t spalign_kmeans_groups_workspace_bytes(int D, int K, int G) {
   return 256;  // the persistent kernel keeps all state on chip
 }
 
-#define KM_LAUNCH(KERNEL, XT, KT, NS2, MINB, ARGS, GRID)                                  \
+#define KM_LAUNCH(KERNEL, XT, KT, NS2, R, MINB, ARGS, GRID)                               \
   do {                                                                                    \
-    int rc__ = set_smem(KERNEL<XT, KT, NS2, MINB>, plan.smem);                            \
+    int rc__ = set_smem(KERNEL<XT, KT, NS2, R, MINB>, plan.smem);                         \
     if (rc__) return rc__;                                                                \
-    KERNEL<XT, KT, NS2, MINB><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS);             \
+    KERNEL<XT, KT, NS2, R, MINB><<<GRID, KM_THREADS, plan.smem, stream>>>(ARGS);          \
   } while (0)
 
 #define KM_DISPATCH(KERNEL, ARGS, GRID)                                                   \
   do {                                                                                    \
-    if (plan.variant == 0) KM_LAUNCH(KERNEL, float, 4, 2, 2, ARGS, GRID);                 \
-    else if (plan.variant == 1) KM_LAUNCH(KERNEL, float, 8, 4, 1, ARGS, GRID);            \
-    else KM_LAUNCH(KERNEL, double, 8, 4, 1, ARGS, GRID);                                  \
+    if (plan.variant == 0 && plan.R == 2) KM_LAUNCH(KERNEL, float, 4, 2, 2, 2, ARGS, GRID); \
+    else if (plan.variant == 0) KM_LAUNCH(KERNEL, float, 4, 2, 4, 1, ARGS, GRID);         \
+    else if (plan.variant == 1 && plan.R == 2) KM_LAUNCH(KERNEL, float, 8, 4, 2, 1, ARGS, GRID); \
+    else if (plan.variant == 1) KM_LAUNCH(KERNEL, float, 8, 4, 1, 1, ARGS, GRID);         \
+    else KM_LAUNCH(KERNEL, double, 8, 4, 1, 1, ARGS, GRID);                               \
   } while (0)
 
 extern "C" int spalign_kmeans_groups(const void* X, int x_dtype, int64_t ldx, int pos_mode,
