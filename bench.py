@@ -296,6 +296,7 @@ def run_ours(args):
     total_images = float(cnt.item())
     value = total_images * args.steps / (ms_max / 1000.0)
 
+    screened, exact_rows = ops.kmeans_debug_stats(reset=True)
     stages = {}
     for name in ('overlap', 'pool', 'init', 'kmeans', 'paint'):
         v = [tm[name][0].elapsed_time(tm[name][1]) for tm in stage_ev if name in tm]
@@ -368,7 +369,8 @@ def run_ours(args):
             'clocks': clocks, 'stages_ms_per_step': stages,
             'kmeans': {'iters_mean': float(iters.mean()), 'iters_max': int(iters.max()),
                        'status_counts': {str(s): int((status == s).sum()) for s in np.unique(status)},
-                       'init_tie_groups': tie_groups},
+                       'init_tie_groups': tie_groups,
+                       'rows_screened_fp32': screened, 'rows_exact_f64': exact_rows},
             'nnz_per_image': nnz / n_img, 'setup_s': t_setup,
             'us_per_image': 1000.0 * ms_max / args.steps / n_img,
         }

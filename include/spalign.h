@@ -161,6 +161,10 @@ int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, i
                           double* centers, int32_t* iters, int32_t* status,
                           spalign_stream_t stream);
 
+/* Diagnostics, synchronises the device: out_host[0] = rows screened in fp32 since the last
+ * reset, out_host[1] = rows that needed the exact float64 pass (host int64[2]). */
+int spalign_kmeans_debug_stats(int64_t* out_host, int reset);
+
 /* Device-side seeded init for many small groups (batch_spalign_kmeans.py:141-149):
  * thr = sort(w_g)[N_g/2]; rows with w > thr -> 0; the others take shuffled[g_shuf_off + i]
  * in row order.  `shuffled` holds, per group, arange(m) % (K-1) + 1 already shuffled by the

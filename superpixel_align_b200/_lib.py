@@ -37,6 +37,7 @@ SIGNATURES = {
                                   _p, _p]),
     'spalign_kmeans_reduce': (_i, [_p, _p, _i, _i, _i, _p, _p]),
     'spalign_kmeans_update': (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    'spalign_kmeans_debug_stats': (_i, [C.POINTER(C.c_int64), _i]),
     'spalign_kmeans_init': (_i, [_p, _p, _i, _p, _p, _p, _p, _p]),
     'spalign_paint': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p]),
     'spalign_refine': (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p]),

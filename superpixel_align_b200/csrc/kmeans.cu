@@ -32,6 +32,9 @@ namespace {
 constexpr int KM_THREADS = 256;
 constexpr int KMAX = 8;
 
+// diagnostics: [0] rows screened, [1] rows sent to the exact float64 pass
+__device__ unsigned long long g_km_stats[2];
+
 struct KmArgs {
   const void* X;
   int64_t ldx;        // row stride in elements
@@ -121,11 +124,11 @@ __device__ __forceinline__ void cp_async_wait() {
 template <typename XT>
 __device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, int64_t row0, int nvalid) {
   const char* src = reinterpret_cast<const char*>(a.X);
-  const int total = nvalid * a.copy16;
-  for (int i = threadIdx.x; i < total; i += KM_THREADS) {
-    const int r = i / a.copy16, c = i - r * a.copy16;
-    cp_async16(buf + (size_t)r * a.srow + (size_t)c * 16,
-               src + ((size_t)(row0 + r) * a.ldx) * sizeof(XT) + (size_t)c * 16);
+  const int lane = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < nvalid; r += KM_THREADS / 32) {
+    const char* g = src + ((size_t)(row0 + r) * a.ldx) * sizeof(XT);
+    char* d = buf + (size_t)r * a.srow;
+    for (int c = lane; c < a.copy16; c += 32) cp_async16(d + (size_t)c * 16, g + (size_t)c * 16);
   }
 }
 
@@ -190,6 +193,13 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       cp_async_wait<0>();
     }
     if (t == 0) *s.namb = 0;
+    // warp 0 prefetches the old assignment and prior weight of its tile row (used in combine B)
+    int pre_a = -1;
+    double pre_w = 0.0;
+    if (t < 32 && t < nvalid && t < TR) {
+      pre_a = assign[trow0 + t];
+      if (mode == 1) pre_w = a.w[trow0 + t];
+    }
     __syncthreads();
     const char* tile = s.buf0 + (size_t)(ti & 1) * s.tile_bytes;
 
@@ -309,6 +319,10 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 
         // ---- exact pass: float64 distances for the undecided rows, whole block per row ----
         const int namb = *s.namb;
+        if (t == 0) {
+          atomicAdd(&g_km_stats[0], (unsigned long long)nvalid);
+          if (namb) atomicAdd(&g_km_stats[1], (unsigned long long)namb);
+        }
         for (int ai = 0; ai < namb; ++ai) {
           const int r = s.amb[ai];
           const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)r * a.srow);
@@ -418,12 +432,12 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       int chg = 0;
       if (valid) {
         const int64_t grow = trow0 + lane;
-        const int a_old = assign[grow];
+        const int a_old = pre_a;
         if (mode == 1) {
           a_new = s.anew[lane];
           chg = a_new != a_old;
-          assign[grow] = a_new;
-          const double wv = a.w[grow];
+          if (chg) assign[grow] = a_new;
+          const double wv = pre_w;
           om = a_new == 0 ? wv : 1.0 - wv;
         } else {
           a_new = a_old;
@@ -987,4 +1001,20 @@ extern "C" int spalign_kmeans_init(const double* w, const int64_t* group_off, in
                   "kmeans_init: bad arguments");
   kmeans_init_kernel<<<G, 256, 0, stream>>>(w, group_off, shuffled, shuf_off, assign, m_out);
   return check_launch("kmeans_init");
+}
+
+// Diagnostics (synchronises the device): out[0] = rows that went through the fp32 screening
+// pass since the last reset, out[1] = rows that needed the exact float64 pass.
+extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
+  unsigned long long h[2] = {0, 0};
+  SPALIGN_CUDA(cudaMemcpyFromSymbol(h, g_km_stats, sizeof(h)));
+  if (out_host) {
+    out_host[0] = (int64_t)h[0];
+    out_host[1] = (int64_t)h[1];
+  }
+  if (reset) {
+    unsigned long long z[2] = {0, 0};
+    SPALIGN_CUDA(cudaMemcpyToSymbol(g_km_stats, z, sizeof(z)));
+  }
+  return SPALIGN_OK;
 }

@@ -407,6 +407,15 @@ class KMeansLarge:
         return KMeansResult(self.assign, self.iters, self.status, self.centers)
 
 
+def kmeans_debug_stats(reset: bool = False):
+    """(rows screened in fp32, rows sent to the exact float64 pass) since the last reset.
+    Synchronises the device."""
+    import ctypes
+    buf = (ctypes.c_int64 * 2)()
+    check(_lib.load().spalign_kmeans_debug_stats(buf, int(reset)), 'kmeans_debug_stats')
+    return int(buf[0]), int(buf[1])
+
+
 def kmeans_init_device(w: torch.Tensor, group_off: torch.Tensor, shuffled: torch.Tensor,
                        shuf_off: torch.Tensor):
     """Seeded init on the device for groups of <= 4096 rows.  Returns (assign int32 [N],
