@@ -51,6 +51,8 @@ struct KmArgs {
   int copy16;         // 16-byte chunks copied per row
   int TR;             // rows per tile (power of two, <= 32)
   int logTR;
+  int Kc;             // clusters the kernel variant is unrolled for (>= K)
+  int part_bytes;     // size of the phase-1 partial-sum scratch
 };
 
 // shared-memory carve-up (all offsets from the dynamic smem base)
@@ -73,7 +75,7 @@ struct KmSmem {
 };
 
 __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
-                                           int Dc) {
+                                           int Dc, int Kc, int part_bytes) {
   size_t o = 0;
   const size_t tile = (size_t)TR * srow;
   if (s) { s->buf0 = base; s->tile_bytes = (int)tile; }
@@ -82,10 +84,11 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   if (s) s->cen = reinterpret_cast<double*>(base + o);
   o += (size_t)K * Dc * sizeof(double);
   if (s) s->cen32 = reinterpret_cast<float*>(base + o);
-  o += (size_t)K * Dc * sizeof(float);
+  o += (size_t)Kc * Dc * sizeof(float);
   o = (o + 15) & ~(size_t)15;
   if (s) s->part = base + o;
-  o += (size_t)KM_THREADS * KMAX * sizeof(double) + 8 * 32 * 33 * sizeof(float);
+  o += (size_t)part_bytes;
+  o = (o + 15) & ~(size_t)15;
   if (s) s->red = reinterpret_cast<double*>(base + o);
   o += (size_t)8 * KMAX * sizeof(double);
   if (s) s->om = reinterpret_cast<double*>(base + o);
@@ -225,15 +228,13 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             xv[r] = *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            if (k < K) {
-              const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
+            const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                float df = xv[r].x - cv.x; a1[r][k] = fmaf(df, df, a1[r][k]);
-                df = xv[r].y - cv.y; a1[r][k] = fmaf(df, df, a1[r][k]);
-                df = xv[r].z - cv.z; a1[r][k] = fmaf(df, df, a1[r][k]);
-                df = xv[r].w - cv.w; a1[r][k] = fmaf(df, df, a1[r][k]);
-              }
+            for (int r = 0; r < R; ++r) {
+              float df = xv[r].x - cv.x; a1[r][k] = fmaf(df, df, a1[r][k]);
+              df = xv[r].y - cv.y; a1[r][k] = fmaf(df, df, a1[r][k]);
+              df = xv[r].z - cv.z; a1[r][k] = fmaf(df, df, a1[r][k]);
+              df = xv[r].w - cv.w; a1[r][k] = fmaf(df, df, a1[r][k]);
             }
           }
         }
@@ -244,13 +245,11 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             xs[r] = reinterpret_cast<const float*>(xw + (size_t)r * a.srow)[d];
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            if (k < K) {
-              const float c = s.cen32[(size_t)k * a.Dc + d];
+            const float c = s.cen32[(size_t)k * a.Dc + d];
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const float df = xs[r] - c;
-                a1[r][k] = fmaf(df, df, a1[r][k]);
-              }
+            for (int r = 0; r < R; ++r) {
+              const float df = xs[r] - c;
+              a1[r][k] = fmaf(df, df, a1[r][k]);
             }
           }
         }
@@ -286,32 +285,30 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             const float px = (float)dpx, py = (float)dpy;
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
-              if (k < K) {
-                const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
-                const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
-                F[k] = fmaf(dx, dx, F[k]);
-                F[k] = fmaf(dy, dy, F[k]);
-              }
+              const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
+              const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
+              F[k] = fmaf(dx, dx, F[k]);
+              F[k] = fmaf(dy, dy, F[k]);
             }
           }
           int j = 0;
           float best = F[0];
 #pragma unroll
           for (int k = 1; k < KT; ++k)
-            if (k < K && F[k] < best) { best = F[k]; j = k; }
+            if (F[k] < best) { best = F[k]; j = k; }
           const float c1 = 2.4e-7f, c2 = 1.6e-5f;
           float B[KT];
           float lim = 0.f;
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            const float cn = c1 * (k < K ? s.cnorm[k] : 0.f);
+            const float cn = c1 * s.cnorm[k];
             B[k] = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
             if (k == j) lim = F[k] + B[k];
           }
-          bool certain = (lim == lim) && (lim < 3.0e38f);
+          bool certain = (lim == lim) && (lim < 3.0e38f) && (j < K);
 #pragma unroll
           for (int k = 0; k < KT; ++k)
-            if (k < K && k != j) certain = certain && (F[k] - B[k] > lim);
+            if (k != j) certain = certain && (F[k] - B[k] > lim);
           s.anew[rr] = certain ? j : -1;
           if (!certain) s.amb[atomicAdd(s.namb, 1)] = rr;
         }
@@ -482,17 +479,17 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 
     // ---- phase 2: centroid sums, cluster by cluster, rows in order ----
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      if (k < K) {
-        const int i1 = s.start[k + 1];
-#pragma unroll 2
-        for (int i = s.start[k]; i < i1; ++i) {
-          const double om = s.om[i];
-          const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
+    for (int sl = 0; sl < NS2; ++sl) {
+      const int c0 = 2 * (sl * KM_THREADS + t);
+      if (c0 + 1 < Dr) {
 #pragma unroll
-          for (int sl = 0; sl < NS2; ++sl) {
-            const int c0 = 2 * (sl * KM_THREADS + t);
-            if (c0 + 1 < Dr) {
+        for (int k = 0; k < KT; ++k) {
+          if (k < K) {
+            const int i1 = s.start[k + 1];
+#pragma unroll 4
+            for (int i = s.start[k]; i < i1; ++i) {
+              const double om = s.om[i];
+              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
               double x0, x1;
               if (kF32) {
                 const float2 v = *reinterpret_cast<const float2*>(xr + c0);
@@ -505,8 +502,17 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
               }
               acc[k][sl][0] = fma(om, x0, acc[k][sl][0]);
               acc[k][sl][1] = fma(om, x1, acc[k][sl][1]);
-            } else if (c0 < Dr) {
-              acc[k][sl][0] = fma(om, (double)xr[c0], acc[k][sl][0]);
+            }
+          }
+        }
+      } else if (c0 < Dr) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (k < K) {
+            const int i1 = s.start[k + 1];
+            for (int i = s.start[k]; i < i1; ++i) {
+              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
+              acc[k][sl][0] = fma(s.om[i], (double)xr[c0], acc[k][sl][0]);
             }
           }
         }
@@ -559,23 +565,28 @@ __device__ __forceinline__ bool finalize_centers(const KmArgs& a, const KmSmem s
   return empty;
 }
 
-// fp32 copies of the centres and ||c_k|| upper bounds for the screening pass
+// fp32 copies of the centres and ||c_k|| upper bounds for the screening pass.  Clusters
+// K..KT-1 of the unrolled kernel get a far-away dummy centre: they never win and never make a
+// row undecided, so the hot loops need no per-cluster guards.
+template <int KT>
 __device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) {
   const int t = threadIdx.x;
-  for (int i = t; i < a.K * a.Dc; i += KM_THREADS) {
-    const int d = i % a.Dc;
-    s.cen32[i] = d < a.D ? (float)s.cen[i] : 0.f;
+  for (int i = t; i < KT * a.Dc; i += KM_THREADS) {
+    const int k = i / a.Dc, d = i - k * a.Dc;
+    s.cen32[i] = k < a.K ? (d < a.D ? (float)s.cen[i] : 0.f) : (d < a.D ? 1.0e15f : 0.f);
   }
   const int wq = t >> 5, lane = t & 31;
-  if (wq < a.K) {
+  if (wq < KT) {
     double sum = 0.0;
-    for (int d = lane; d < a.D; d += 32) {
-      const double c = s.cen[(size_t)wq * a.Dc + d];
-      sum = fma(c, c, sum);
+    if (wq < a.K) {
+      for (int d = lane; d < a.D; d += 32) {
+        const double c = s.cen[(size_t)wq * a.Dc + d];
+        sum = fma(c, c, sum);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s.cnorm[wq] = (float)sqrt(sum) * 1.000001f;
+    if (lane == 0) s.cnorm[wq] = wq < a.K ? (float)sqrt(sum) * 1.000001f : 0.f;
   }
   __syncthreads();
 }
@@ -594,7 +605,7 @@ template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
   const int grp = blockIdx.x;
   const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
   const int t = threadIdx.x;
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
     ++it;
     zero_acc<KT, NS2>(acc);
     if (t == 0) *s.changed = 0;
-    if (sizeof(XT) == 4) prepare_screen(g.a, s);
+    if (sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
     __syncthreads();
     km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 1, g.assign, acc);
     const int changed = *s.changed;  // km_sweep ends with __syncthreads
@@ -656,7 +667,7 @@ template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
   const int ck = blockIdx.x;
   const int grp = (int)g.chunks[(size_t)ck * 3];
   const int64_t rb = g.chunks[(size_t)ck * 3 + 1], re = g.chunks[(size_t)ck * 3 + 2];
@@ -674,7 +685,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   __syncthreads();
-  if (g.mode == 1 && sizeof(XT) == 4) prepare_screen(g.a, s);
+  if (g.mode == 1 && sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
   km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc);
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
@@ -821,6 +832,8 @@ struct Plan {
   int srow;
   int copy16;
   int Dc;
+  int Kc;
+  int part_bytes;
   size_t smem;
 };
 
@@ -836,19 +849,21 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
   const bool small = x_dtype == SPALIGN_F32 && K <= 4 && Dr <= 1024;
   p->variant = x_dtype == SPALIGN_F64 ? 2 : (small ? 0 : 1);
   const size_t limit = (size_t)200 * 1024;
+  p->Kc = small ? 4 : 8;
   if (p->variant == 2) {
     for (int tr = 32, lg = 5; tr >= 2; tr >>= 1, --lg) {
-      size_t bytes = km_carve(nullptr, nullptr, tr, srow, K, p->Dc);
+      const int pb = KM_THREADS * p->Kc * (int)sizeof(double);
+      size_t bytes = km_carve(nullptr, nullptr, tr, srow, K, p->Dc, p->Kc, pb);
       if (bytes <= limit) {
-        p->TR = tr; p->logTR = lg; p->R = 1; p->smem = bytes;
+        p->TR = tr; p->logTR = lg; p->R = 1; p->part_bytes = pb; p->smem = bytes;
         return true;
       }
     }
     return false;
   }
-  // fp32: TR = 8*R.  Variant 0 prefers R=2 (two CTAs per SM, fp32 and fp64 phases of the two
-  // CTAs overlap) unless SPALIGN_KM_R=4 asks for the bigger tile; variant 1 takes R=2 then 1.
-  int want = small ? 2 : 2;
+  // fp32: TR = 8*R.  Variant 0 prefers R=2 (two CTAs per SM, so the fp32 and fp64 phases of the
+  // two CTAs overlap) unless SPALIGN_KM_R=4 asks for the bigger tile; variant 1: R=2 then 1.
+  int want = 2;
   if (const char* e = getenv("SPALIGN_KM_R")) {
     int v = atoi(e);
     if (small && (v == 2 || v == 4)) want = v;
@@ -858,9 +873,11 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
     int r = cands[i];
     if (!small && r == 4) continue;
     if (small && r == 1) continue;
-    size_t bytes = km_carve(nullptr, nullptr, 8 * r, srow, K, p->Dc);
+    const int pb = (KM_THREADS / 32) * (r * p->Kc) * 33 * (int)sizeof(float);
+    size_t bytes = km_carve(nullptr, nullptr, 8 * r, srow, K, p->Dc, p->Kc, pb);
     if (bytes <= limit) {
-      p->R = r; p->TR = 8 * r; p->logTR = r == 4 ? 5 : (r == 2 ? 4 : 3); p->smem = bytes;
+      p->R = r; p->TR = 8 * r; p->logTR = r == 4 ? 5 : (r == 2 ? 4 : 3);
+      p->part_bytes = pb; p->smem = bytes;
       return true;
     }
   }
@@ -883,7 +900,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->X = X; a->ldx = ldx; a->pos_mode = pos_mode; a->pos_w = pos_w ? pos_w : 1;
   a->pos_period = pos_period ? pos_period : 1; a->pos_row0 = pos_row0; a->w = w;
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
-  a->TR = p.TR; a->logTR = p.logTR;
+  a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
   return SPALIGN_OK;
 }
 
