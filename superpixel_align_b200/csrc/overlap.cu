@@ -21,7 +21,7 @@ namespace spalign {
 namespace {
 
 constexpr int EMIT_THREADS = 128;
-constexpr int STAGE_CAP = 1024;     // pairs staged per block
+constexpr int STAGE_CAP = 896;      // pairs staged per block
 constexpr int WARP_TIER_MAX = 256;  // rows up to this many cells are sorted by one warp
 constexpr int SCAN_TILE = 2048;
 constexpr int HEAVY_SLOTS = 32;
@@ -160,6 +160,7 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                const double* __restrict__ gx, int cap_img, OverlapWs ws, int64_t* sum_y,
                int64_t* sum_x, int64_t* nnz_flags) {
   __shared__ PairStage st;
+  __shared__ double sP[EMIT_THREADS][9];
   const int img = blockIdx.y;
   const int ncell = fh * fw;
   const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
@@ -184,36 +185,35 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           longlong2 a = __ldg(q + h);
-          v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;
+          v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;  // -1: out of range
           v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
         }
       }
     }
-    unsigned mlo = 0, mhi = 0;  // valid-pixel mask
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      mlo |= ((unsigned)v[j] < (unsigned)n_sp) ? (1u << j) : 0u;
-      mhi |= ((unsigned)v[32 + j] < (unsigned)n_sp) ? (1u << j) : 0u;
-    }
-    unsigned long long remaining = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
-    bad = remaining != ~0ull;
-    if (bad)
-      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
-               (unsigned long long)SPALIGN_F_LABEL_RANGE);
-    double gyl[8], gxl[8];
+    // prefix sums of the cell's 8 column factors: a contiguous run j0..j1-1 of a pixel row
+    // sums to P[j1] - P[j0] (one DADD instead of eight masked ones)
     const bool have_prior = gy != nullptr;
+    double gyl[8], gxl[8];
+    double* P = sP[threadIdx.x];
     if (have_prior) {
+      double run = 0.0;
+      P[0] = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         gyl[k] = gy[cy * 8 + k];
         gxl[k] = gx[cx * 8 + k];
+        run = __dadd_rn(run, gxl[k]);
+        P[k + 1] = run;
       }
     }
+    unsigned long long remaining = ~0ull;
     while (remaining) {
       const int i = __ffsll((long long)remaining) - 1;
       int L = v[0];
+      if (i != 0) {
 #pragma unroll
-      for (int j = 1; j < 64; ++j) L = (i == j) ? v[j] : L;
+        for (int j = 1; j < 64; ++j) L = (i == j) ? v[j] : L;
+      }
       unsigned lo = 0, hi = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -221,6 +221,11 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
         hi |= (v[32 + j] == L) ? (1u << j) : 0u;
       }
       const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      remaining &= ~m;
+      if ((unsigned)L >= (unsigned)n_sp) {  // label outside [0, n_sp): flag it, emit nothing
+        bad = true;
+        continue;
+      }
       const int cnt = __popc(lo) + __popc(hi);
       int syl = 0, sxl = 0;
 #pragma unroll
@@ -232,17 +237,27 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const unsigned b = (unsigned)(m >> (8 * r)) & 0xffu;
-          double rs = 0.0;
+          if (b == 0u) continue;
+          const int j0 = __ffs(b) - 1;
+          const int n = __popc(b);
+          double rs;
+          if ((b >> j0) == ((1u << n) - 1u)) {  // contiguous run (the usual case)
+            rs = __dadd_rn(P[j0 + n], -P[j0]);
+          } else {
+            rs = 0.0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rs = __dadd_rn(rs, ((b >> j) & 1u) ? gxl[j] : 0.0);
+            for (int j = 0; j < 8; ++j) rs = __dadd_rn(rs, ((b >> j) & 1u) ? gxl[j] : 0.0);
+          }
           pr = __fma_rn(gyl[r], rs, pr);
         }
       }
       stage_pair(st, ws, img, cap_img, (int)(row0 + L), c, cnt,
                  (long long)cnt * (cy * 8) + syl, (long long)cnt * (cx * 8) + sxl, pr, sum_y,
                  sum_x, nnz_flags);
-      remaining &= ~m;
     }
+    if (bad)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_LABEL_RANGE);
   }
   flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
 }

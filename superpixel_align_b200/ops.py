@@ -74,6 +74,20 @@ def prior_axes(H, W, y_rel_pos, x_rel_pos, y_rel_sigma, x_rel_sigma):
     return gy, gx
 
 
+_CONST_CACHE = {}
+
+
+def _cached_const(key, make):
+    """Small per-device cache of read-only device constants (prior factors, row offsets) so
+    repeated batches of the same shape do not pay a pageable host->device copy each."""
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) > 64:
+            _CONST_CACHE.clear()
+        t = _CONST_CACHE[key] = make()
+    return t
+
+
 @dataclass
 class Overlap:
     """CSR overlap matrix of a batch + per-superpixel statistics (device tensors)."""
@@ -136,16 +150,18 @@ def overlap_csr(labels: torch.Tensor, fh: int, fw: int, n_sp: Sequence[int],
     assert len(n_sp) == n, 'one superpixel count per image'
     sp_off_host = np.concatenate([[0], np.cumsum(n_sp)]).astype(np.int64)
     n_rows = int(sp_off_host[-1])
-    sp_off = torch.from_numpy(sp_off_host).to(dev, non_blocking=True)
+    sp_off = _cached_const(('sp_off', dev, sp_off_host.tobytes()),
+                           lambda: torch.from_numpy(sp_off_host).to(dev))
     ncell = fh * fw
     if nnz_cap_per_image is None:
         nnz_cap_per_image = min(H * W, 3 * ncell + 2 * int(n_sp.max()) + 1024)
     cap = int(nnz_cap_per_image) * n
     gy = gx = None
     if prior is not None:
-        gy_h, gx_h = prior_axes(H, W, *prior)
-        gy = torch.from_numpy(gy_h).to(dev, non_blocking=True)
-        gx = torch.from_numpy(gx_h).to(dev, non_blocking=True)
+        def make():
+            gy_h, gx_h = prior_axes(H, W, *prior)
+            return torch.from_numpy(gy_h).to(dev), torch.from_numpy(gx_h).to(dev)
+        gy, gx = _cached_const(('prior', dev, H, W, tuple(float(p) for p in prior)), make)
     lib = _lib.load()
     ws_bytes = lib.spalign_overlap_workspace_bytes(n, H, W, fh, fw, n_rows, cap)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
