@@ -142,8 +142,6 @@ __device__ __forceinline__ void flush_stage(PairStage& st, const OverlapWs& ws, 
   int n = min(st.count, STAGE_CAP);
   if (threadIdx.x == 0) {
     st.base = n ? atomicAdd(&ws.pair_count[img], n) : 0;
-    // high-water mark of pairs per image, so a caller can size nnz_cap after an overflow
-    if (n) atomicMax(reinterpret_cast<long long*>(&nnz_flags[2]), (long long)st.base + n);
   }
   __syncthreads();
   int base = st.base;
@@ -153,6 +151,39 @@ __device__ __forceinline__ void flush_stage(PairStage& st, const OverlapWs& ws, 
 }
 
 // Fast path: 8x8-pixel cells (DRN stride 8), one thread owns one cell in registers.
+template <typename LabelT, bool kStream>
+__device__ __forceinline__ void load_cell_s8(const LabelT* __restrict__ p, int W, int n_sp,
+                                             int (&v)[64]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (sizeof(LabelT) == 4) {
+      int4 a, b;
+      if (kStream) {
+        a = ld_stream_int4(p + (size_t)r * W);
+        b = ld_stream_int4(p + (size_t)r * W + 4);
+      } else {
+        a = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
+        b = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W + 4));
+      }
+      v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
+      v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
+    } else {
+      const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        longlong2 a = __ldg(q + h);
+        v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;  // -1: out of range
+        v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+      }
+    }
+  }
+}
+
+// Two phases per block: (A) every thread loads its cell and handles it on the spot when all 64
+// pixels carry one label (about two thirds of the cells of a SLIC map); cells holding several
+// labels are listed in shared memory and (B) re-read densely, one listed cell per thread, by
+// the general loop that peels one distinct label per iteration with a 64-bit match mask.
+// Splitting keeps the expensive loop off the warps that only hold uniform cells.
 template <typename LabelT>
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
@@ -161,38 +192,59 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                int64_t* sum_x, int64_t* nnz_flags) {
   __shared__ PairStage st;
   __shared__ double sP[EMIT_THREADS][9];
+  __shared__ int s_mixed[EMIT_THREADS];
+  __shared__ int s_nmixed;
   const int img = blockIdx.y;
   const int ncell = fh * fw;
-  const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
-  if (threadIdx.x == 0) st.count = 0;
+  if (threadIdx.x == 0) {
+    st.count = 0;
+    s_nmixed = 0;
+  }
   __syncthreads();
   const int64_t row0 = sp_off[img];
   const int n_sp = (int)(sp_off[img + 1] - row0);
-  if (c < ncell) {
-    const int cy = c / fw, cx = c - cy * fw;
-    const LabelT* p = labels + ((size_t)img * H + (size_t)cy * 8) * W + (size_t)cx * 8;
-    int v[64];
-    bool bad = false;
+  const bool have_prior = gy != nullptr;
+  const LabelT* img_labels = labels + (size_t)img * H * W;
+  bool bad = false;
+  int v[64];
+  {  // ---- phase A ----
+    const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
+    if (c < ncell) {
+      const int cy = c / fw, cx = c - cy * fw;
+      load_cell_s8<LabelT, true>(img_labels + ((size_t)cy * 8) * W + (size_t)cx * 8, W, n_sp, v);
+      int diff = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (sizeof(LabelT) == 4) {
-        int4 a = ld_stream_int4(p + (size_t)r * W);
-        int4 b = ld_stream_int4(p + (size_t)r * W + 4);
-        v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
-        v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
-      } else {
-        const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+      for (int j = 1; j < 64; ++j) diff |= v[j] ^ v[0];
+      if (diff == 0) {
+        const int L = v[0];
+        if ((unsigned)L >= (unsigned)n_sp) {
+          bad = true;
+        } else {
+          double pr = 0.0;
+          if (have_prior) {
+            double rs = 0.0;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          longlong2 a = __ldg(q + h);
-          v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;  // -1: out of range
-          v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+            for (int k = 0; k < 8; ++k) rs = __dadd_rn(rs, gx[cx * 8 + k]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pr = __fma_rn(gy[cy * 8 + k], rs, pr);
+          }
+          stage_pair(st, ws, img, cap_img, (int)(row0 + L), c, 64, 64LL * (cy * 8) + 224,
+                     64LL * (cx * 8) + 224, pr, sum_y, sum_x, nnz_flags);
         }
+      } else {
+        s_mixed[atomicAdd(&s_nmixed, 1)] = c;
       }
     }
-    // prefix sums of the cell's 8 column factors: a contiguous run j0..j1-1 of a pixel row
-    // sums to P[j1] - P[j0] (one DADD instead of eight masked ones)
-    const bool have_prior = gy != nullptr;
+  }
+  __syncthreads();
+  // ---- phase B: cells with several labels, densely packed over the threads ----
+  const int nmixed = s_nmixed;
+  for (int idx = threadIdx.x; idx < nmixed; idx += EMIT_THREADS) {
+    const int c = s_mixed[idx];
+    const int cy = c / fw, cx = c - cy * fw;
+    load_cell_s8<LabelT, false>(img_labels + ((size_t)cy * 8) * W + (size_t)cx * 8, W, n_sp, v);
+    // prefix sums of the cell's 8 column factors: a contiguous run j0..j0+n-1 of a pixel row
+    // sums to P[j0+n] - P[j0] (one DADD instead of eight masked ones)
     double gyl[8], gxl[8];
     double* P = sP[threadIdx.x];
     if (have_prior) {
@@ -255,10 +307,10 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                  (long long)cnt * (cy * 8) + syl, (long long)cnt * (cx * 8) + sxl, pr, sum_y,
                  sum_x, nnz_flags);
     }
-    if (bad)
-      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
-               (unsigned long long)SPALIGN_F_LABEL_RANGE);
   }
+  if (bad)
+    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+             (unsigned long long)SPALIGN_F_LABEL_RANGE);
   flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
 }
 
@@ -379,7 +431,15 @@ scan_tile_sums_kernel(const int* __restrict__ row_nnz, int64_t R, int* tile_sum)
 __global__ void __launch_bounds__(256)
 scan_finish_kernel(const int* __restrict__ row_nnz, int64_t R, const int* __restrict__ tile_sum,
                    int n_tiles, int* indptr, int64_t* nnz_flags, int64_t nnz_cap,
-                   int* heavy_rows, int* heavy_count, int heavy_cap) {
+                   int* heavy_rows, int* heavy_count, int heavy_cap,
+                   const int* __restrict__ pair_count, int n_img) {
+  if (blockIdx.x == 0) {  // high-water mark of pairs per image (sizes nnz_cap after an overflow)
+    int mx = 0;
+    for (int i = threadIdx.x; i < n_img; i += 256) mx = max(mx, pair_count[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane_id() == 0 && mx > 0) atomicMax(reinterpret_cast<long long*>(&nnz_flags[2]), (long long)mx);
+  }
   __shared__ long long s_prefix;
   // prefix of the tiles before this one
   long long pre = 0;
@@ -675,7 +735,8 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
   scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum);
   scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum, n_tiles,
                                                   indptr, nnz_flags, nnz_cap, ws.heavy_rows,
-                                                  ws.heavy_count, ws.heavy_cap);
+                                                  ws.heavy_count, ws.heavy_cap, ws.pair_count,
+                                                  n_img);
   int sgx = (cap_img + 256 * 4 - 1) / (256 * 4);
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
