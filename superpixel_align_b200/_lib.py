@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libspalign_b200.so')
+LIB_PATH = os.environ.get('SPALIGN_LIB', os.path.join(_HERE, 'libspalign_b200.so'))
 
 I32, I64, U8 = 0, 1, 2
 F32, F64 = 0, 1

@@ -21,7 +21,10 @@ namespace spalign {
 namespace {
 
 constexpr int EMIT_THREADS = 128;
-constexpr int STAGE_CAP = 896;      // pairs staged per block
+#ifndef EMIT_MIN_BLOCKS
+#define EMIT_MIN_BLOCKS 4  // 128 registers, no spills: four resident blocks per SM
+#endif
+constexpr int STAGE_CAP = 768;      // pairs staged per block
 constexpr int WARP_TIER_MAX = 256;  // rows up to this many cells are sorted by one warp
 constexpr int SCAN_TILE = 2048;
 constexpr int HEAVY_SLOTS = 32;
@@ -151,118 +154,77 @@ __device__ __forceinline__ void flush_stage(PairStage& st, const OverlapWs& ws, 
 }
 
 // Fast path: 8x8-pixel cells (DRN stride 8), one thread owns one cell in registers.
-template <typename LabelT, bool kStream>
-__device__ __forceinline__ void load_cell_s8(const LabelT* __restrict__ p, int W, int n_sp,
-                                             int (&v)[64]) {
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if (sizeof(LabelT) == 4) {
-      int4 a, b;
-      if (kStream) {
-        a = ld_stream_int4(p + (size_t)r * W);
-        b = ld_stream_int4(p + (size_t)r * W + 4);
-      } else {
-        a = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
-        b = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W + 4));
-      }
-      v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
-      v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
-    } else {
-      const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        longlong2 a = __ldg(q + h);
-        v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;  // -1: out of range
-        v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
-      }
-    }
-  }
-}
-
-// Two phases per block: (A) every thread loads its cell and handles it on the spot when all 64
-// pixels carry one label (about two thirds of the cells of a SLIC map); cells holding several
-// labels are listed in shared memory and (B) re-read densely, one listed cell per thread, by
-// the general loop that peels one distinct label per iteration with a 64-bit match mask.
-// Splitting keeps the expensive loop off the warps that only hold uniform cells.
 template <typename LabelT>
-__global__ void __launch_bounds__(EMIT_THREADS)
+__global__ void __launch_bounds__(EMIT_THREADS, EMIT_MIN_BLOCKS)
 emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                const int64_t* __restrict__ sp_off, const double* __restrict__ gy,
                const double* __restrict__ gx, int cap_img, OverlapWs ws, int64_t* sum_y,
                int64_t* sum_x, int64_t* nnz_flags) {
   __shared__ PairStage st;
-  __shared__ double sP[EMIT_THREADS][9];
-  __shared__ int s_mixed[EMIT_THREADS];
-  __shared__ int s_nmixed;
   const int img = blockIdx.y;
   const int ncell = fh * fw;
-  if (threadIdx.x == 0) {
-    st.count = 0;
-    s_nmixed = 0;
-  }
+  const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  if (threadIdx.x == 0) st.count = 0;
   __syncthreads();
   const int64_t row0 = sp_off[img];
   const int n_sp = (int)(sp_off[img + 1] - row0);
-  const bool have_prior = gy != nullptr;
-  const LabelT* img_labels = labels + (size_t)img * H * W;
-  bool bad = false;
-  int v[64];
-  {  // ---- phase A ----
-    const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
-    if (c < ncell) {
-      const int cy = c / fw, cx = c - cy * fw;
-      load_cell_s8<LabelT, true>(img_labels + ((size_t)cy * 8) * W + (size_t)cx * 8, W, n_sp, v);
-      int diff = 0;
+  if (c < ncell) {
+    const int cy = c / fw, cx = c - cy * fw;
+    const LabelT* p = labels + ((size_t)img * H + (size_t)cy * 8) * W + (size_t)cx * 8;
+    int v[64];
+    bool bad = false;
 #pragma unroll
-      for (int j = 1; j < 64; ++j) diff |= v[j] ^ v[0];
-      if (diff == 0) {
-        const int L = v[0];
-        if ((unsigned)L >= (unsigned)n_sp) {
-          bad = true;
-        } else {
-          double pr = 0.0;
-          if (have_prior) {
-            double rs = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) rs = __dadd_rn(rs, gx[cx * 8 + k]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) pr = __fma_rn(gy[cy * 8 + k], rs, pr);
-          }
-          stage_pair(st, ws, img, cap_img, (int)(row0 + L), c, 64, 64LL * (cy * 8) + 224,
-                     64LL * (cx * 8) + 224, pr, sum_y, sum_x, nnz_flags);
-        }
+    for (int r = 0; r < 8; ++r) {
+      if (sizeof(LabelT) == 4) {
+        int4 a = ld_stream_int4(p + (size_t)r * W);
+        int4 b = ld_stream_int4(p + (size_t)r * W + 4);
+        v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
+        v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
       } else {
-        s_mixed[atomicAdd(&s_nmixed, 1)] = c;
+        const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          longlong2 a = __ldg(q + h);
+          v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;
+          v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+        }
       }
     }
-  }
-  __syncthreads();
-  // ---- phase B: cells with several labels, densely packed over the threads ----
-  const int nmixed = s_nmixed;
-  for (int idx = threadIdx.x; idx < nmixed; idx += EMIT_THREADS) {
-    const int c = s_mixed[idx];
-    const int cy = c / fw, cx = c - cy * fw;
-    load_cell_s8<LabelT, false>(img_labels + ((size_t)cy * 8) * W + (size_t)cx * 8, W, n_sp, v);
-    // prefix sums of the cell's 8 column factors: a contiguous run j0..j0+n-1 of a pixel row
-    // sums to P[j0+n] - P[j0] (one DADD instead of eight masked ones)
+    unsigned long long remaining = ~0ull;  // label validity is checked once per distinct label
     double gyl[8], gxl[8];
-    double* P = sP[threadIdx.x];
+    const bool have_prior = gy != nullptr;
+    double cell_prior = 0.0;  // prior of the whole cell: sum_r gy[r] * (sum_j gx[j])
     if (have_prior) {
-      double run = 0.0;
-      P[0] = 0.0;
+      double gx8 = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         gyl[k] = gy[cy * 8 + k];
         gxl[k] = gx[cx * 8 + k];
-        run = __dadd_rn(run, gxl[k]);
-        P[k + 1] = run;
+        gx8 = __dadd_rn(gx8, gxl[k]);
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cell_prior = __fma_rn(gyl[k], gx8, cell_prior);
     }
-    unsigned long long remaining = ~0ull;
+    double emitted_prior = 0.0;  // prior already attributed to earlier labels of this cell
+    bool can_complement = true;
+    bool first = true;
     while (remaining) {
-      const int i = __ffsll((long long)remaining) - 1;
-      int L = v[0];
-      if (i != 0) {
+      // next label: the first still-unprocessed pixel among a few fixed positions (corners,
+      // edge and centre pixels -- static register indices), else the first unprocessed pixel
+      int L = 0;
+      bool found = false;
+#define SPALIGN_CAND(p)                                  \
+  if (!found && ((remaining >> (p)) & 1ull)) {            \
+    L = v[p];                                             \
+    found = true;                                         \
+  }
+      SPALIGN_CAND(0) SPALIGN_CAND(7) SPALIGN_CAND(56) SPALIGN_CAND(63) SPALIGN_CAND(3)
+      SPALIGN_CAND(60) SPALIGN_CAND(24) SPALIGN_CAND(31) SPALIGN_CAND(32) SPALIGN_CAND(39)
+      SPALIGN_CAND(27) SPALIGN_CAND(36)
+#undef SPALIGN_CAND
+      if (!found) {
+        const int i = __ffsll((long long)remaining) - 1;
+        L = v[0];
 #pragma unroll
         for (int j = 1; j < 64; ++j) L = (i == j) ? v[j] : L;
       }
@@ -276,6 +238,8 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
       remaining &= ~m;
       if ((unsigned)L >= (unsigned)n_sp) {  // label outside [0, n_sp): flag it, emit nothing
         bad = true;
+        can_complement = false;
+        first = false;
         continue;
       }
       const int cnt = __popc(lo) + __popc(hi);
@@ -286,31 +250,31 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
       for (int j = 0; j < 8; ++j) sxl += j * __popcll((m >> j) & 0x0101010101010101ull);
       double pr = 0.0;
       if (have_prior) {
+        if (remaining == 0ull && can_complement) {
+          // last label of the cell: whole-cell prior minus what the other labels took
+          // (a cell with a single label gets cell_prior itself)
+          pr = first ? cell_prior : __dadd_rn(cell_prior, -emitted_prior);
+        } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const unsigned b = (unsigned)(m >> (8 * r)) & 0xffu;
-          if (b == 0u) continue;
-          const int j0 = __ffs(b) - 1;
-          const int n = __popc(b);
-          double rs;
-          if ((b >> j0) == ((1u << n) - 1u)) {  // contiguous run (the usual case)
-            rs = __dadd_rn(P[j0 + n], -P[j0]);
-          } else {
-            rs = 0.0;
+          for (int r = 0; r < 8; ++r) {
+            const unsigned b = (unsigned)(m >> (8 * r)) & 0xffu;
+            double rs = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) rs = __dadd_rn(rs, ((b >> j) & 1u) ? gxl[j] : 0.0);
+            pr = __fma_rn(gyl[r], rs, pr);
           }
-          pr = __fma_rn(gyl[r], rs, pr);
+          emitted_prior = __dadd_rn(emitted_prior, pr);
         }
       }
+      first = false;
       stage_pair(st, ws, img, cap_img, (int)(row0 + L), c, cnt,
                  (long long)cnt * (cy * 8) + syl, (long long)cnt * (cx * 8) + sxl, pr, sum_y,
                  sum_x, nnz_flags);
     }
+    if (bad)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_LABEL_RANGE);
   }
-  if (bad)
-    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
-             (unsigned long long)SPALIGN_F_LABEL_RANGE);
   flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
 }
 
