@@ -380,58 +380,54 @@ def run_ours(args):
 
 
 def run_e2e(args, dev, labels, feats, world):
-    """Same metric through the drop-in API (batch_superpixel_align -> batch_create_prior ->
-    batch_weighted_kmeans, batchsize 1 = per-image clustering) with inputs in pinned HOST
-    memory and the result masks copied back to the host, every step."""
-    import types
+    """Same metric end to end through the public host-buffer API
+    (superpixel_align_b200.pipeline.HostPipeline): every step copies the step's label maps
+    (int32) and cell-major feature maps (fp32) from pinned HOST memory to the device, runs the
+    hot path with per-image clustering, and copies the uint8 cluster maps and road masks back
+    to pinned host memory; copies and compute overlap on two streams."""
     import torch
     import torch.distributed as dist
-    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    from superpixel_align_b200 import pipeline
     n_img = labels.shape[0]
     pool_n = min(args.host_pool, n_img)
-    h_lab = [labels[i:i + 1].cpu().pin_memory() for i in range(pool_n)]
-    # host features in channels_last [1, C, fh, fw] (cell-major bytes)
-    h_feat = [feats[i].reshape(1, FH, FW, C).permute(0, 3, 1, 2).cpu().pin_memory()
-              for i in range(pool_n)]
-    a = types.SimpleNamespace(gpu=dev.index, n_clusters=K, without_pos=False, y_rel_pos=PRIOR[0],
-                              x_rel_pos=PRIOR[1], y_rel_sigma=PRIOR[2], x_rel_sigma=PRIOR[3])
-    n_e2e = min(args.e2e_images, n_img)
+    sub = min(args.e2e_sub_batch, pool_n)
+    h_lab = labels[:pool_n].cpu().pin_memory()
+    h_feat = feats[:pool_n].cpu().pin_memory()
+    n_e2e = max(sub, (min(args.e2e_images, n_img) // sub) * sub)
+    batches = []
+    for i in range(0, n_e2e, sub):
+        j = i % (pool_n - sub + 1) if pool_n > sub else 0
+        batches.append((h_lab[j:j + sub], h_feat[j:j + sub], [GY * GX] * sub))
+    hp = pipeline.HostPipeline(H, W, FH, FW, C, sub_batch=sub, k=K, prior=PRIOR, device=dev)
+    sink = {'road_px': 0}
 
-    def one(i):
-        lab, feat = h_lab[i % pool_n], h_feat[i % pool_n]
-        bsk.clear_cache()
-        lab_d = lab.to(dev, non_blocking=True)
-        f, n_per = bsk.batch_superpixel_align(a, None, None, lab_d,
-                                              feat.to(dev, non_blocking=True))
-        w = bsk.batch_create_prior(a, lab_d)
-        cres, road = bsk.batch_weighted_kmeans(a, lab_d, f, w, n_per)
-        return cres.to(torch.uint8).cpu(), road.cpu()
+    def on_result(i, cmap, mask):
+        sink['road_px'] += int(mask[0, ::64, ::64].sum())     # touch the host copy
 
     np.random.seed(1111)
-    for i in range(3):
-        c, r = one(i)
+    hp.process(batches[:3], on_result)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    hp.h2d_bytes = hp.d2h_bytes = 0
     t0 = time.time()
     for _ in range(args.steps):
-        for i in range(n_e2e):
-            c, r = one(i)
+        hp.process(batches, on_result)
     torch.cuda.synchronize()
     dt = time.time() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    h2d = n_e2e * (H * W * 4 + FH * FW * C * 4)
-    d2h = n_e2e * (H * W + H * W)
     return {'value': world * n_e2e * args.steps / dt, 'unit': 'images/s',
-            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-            'images_per_step': n_e2e,
-            'api': 'superpixel_align_b200.batch_spalign_kmeans.{batch_superpixel_align,'
-                   'batch_create_prior,batch_weighted_kmeans}, one image per call (batchsize 1), '
-                   'pinned host label map int32 + channels_last fp32 features in, uint8 cluster '
-                   'map + bool road mask out'}
+            'h2d_bytes_per_step': hp.h2d_bytes // args.steps,
+            'd2h_bytes_per_step': hp.d2h_bytes // args.steps,
+            'images_per_step': n_e2e, 'sub_batch': sub,
+            'h2d_GBps': hp.h2d_bytes / dt / 1e9,
+            'api': 'superpixel_align_b200.pipeline.HostPipeline.process: pinned host int32 label '
+                   'maps + fp32 cell-major (channels_last) feature maps in, uint8 cluster maps + '
+                   'road masks out to pinned host memory; double-buffered copy/compute streams; '
+                   'per-image clustering'}
 
 
 def main():
@@ -441,8 +437,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--images', type=int, default=300, help='images per GPU per step')
-    ap.add_argument('--e2e-images', type=int, default=60, help='images per e2e step')
-    ap.add_argument('--host-pool', type=int, default=8, help='distinct pinned host images')
+    ap.add_argument('--e2e-images', type=int, default=96, help='images per e2e step')
+    ap.add_argument('--e2e-sub-batch', type=int, default=8, help='images per host->device sub-batch')
+    ap.add_argument('--host-pool', type=int, default=16, help='distinct pinned host images')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

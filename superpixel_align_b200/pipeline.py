@@ -126,3 +126,93 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
     mark('paint', False)
     return PipelineOutput(cmap, mask, res.assign, feats, weights, res.iters, res.status, m, ov,
                           group_off_host, m_exp)
+
+
+class HostPipeline:
+    """End-to-end path for inputs that live in HOST memory (pinned): label maps and cell-major
+    feature maps go host -> device on a copy stream while the previous sub-batch is being
+    processed on the compute stream, and the resulting cluster maps / road masks come back
+    device -> host on the copy stream.  Two device slots and two pinned result slots are
+    reused, so nothing is allocated in steady state.
+
+        hp = HostPipeline(H, W, fh, fw, C, sub_batch=6)
+        hp.process([(labels_cpu, feats_cpu, n_sp), ...], on_result=lambda i, cmap, mask: ...)
+
+    ``labels_cpu`` [b, H, W] int32 and ``feats_cpu`` [b, fh*fw, C] float32 are pinned CPU
+    tensors with b <= sub_batch; ``on_result`` receives pinned uint8 CPU tensors that are only
+    valid during the callback.
+    """
+
+    def __init__(self, H, W, fh, fw, C, sub_batch=6, k=4, prior=(0.75, 0.5, 0.1, 0.1),
+                 append_pos=True, device=None, label_dtype=torch.int32):
+        self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.shape = (H, W, fh, fw, C)
+        self.k, self.prior, self.append_pos, self.B = k, prior, append_pos, sub_batch
+        d = self.dev
+        self.lab = [torch.empty((sub_batch, H, W), dtype=label_dtype, device=d) for _ in range(2)]
+        self.feat = [torch.empty((sub_batch, fh * fw, C), dtype=torch.float32, device=d)
+                     for _ in range(2)]
+        self.out_c = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.out_m = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.copy = torch.cuda.Stream(device=d)
+        self.comp = torch.cuda.Stream(device=d)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _upload(self, slot, labels_cpu, feats_cpu, free_event):
+        b = labels_cpu.shape[0]
+        with torch.cuda.stream(self.copy):
+            if free_event is not None:
+                self.copy.wait_event(free_event)      # slot's previous occupant is done
+            self.lab[slot][:b].copy_(labels_cpu, non_blocking=True)
+            self.feat[slot][:b].copy_(feats_cpu, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        self.h2d_bytes += labels_cpu.numel() * labels_cpu.element_size() + \
+            feats_cpu.numel() * feats_cpu.element_size()
+        return ev
+
+    def process(self, batches, on_result=None):
+        H, W, fh, fw, C = self.shape
+        batches = list(batches)
+        n = len(batches)
+        if n == 0:
+            return
+        comp_done = [None, None]     # compute finished reading device slot s
+        d2h_done = [None, None]      # pinned result slot s has been consumed / is free
+        up = self._upload(0, batches[0][0], batches[0][1], None)
+        pending = None               # (index, slot, b, event) of the D2H in flight
+        for i in range(n):
+            s = i & 1
+            labels_cpu, feats_cpu, n_sp = batches[i]
+            b = labels_cpu.shape[0]
+            nxt = None
+            if i + 1 < n:                # prefetch the next sub-batch while this one computes
+                nxt = self._upload(s ^ 1, batches[i + 1][0], batches[i + 1][1], comp_done[s ^ 1])
+            with torch.cuda.stream(self.comp):
+                self.comp.wait_event(up)
+                out = run_batch(self.lab[s][:b], self.feat[s][:b], n_sp, fh, fw, k=self.k,
+                                prior=self.prior, append_pos=self.append_pos)
+                ev_c = torch.cuda.Event()
+                ev_c.record(self.comp)
+            comp_done[s] = ev_c
+            if pending is not None:      # hand the previous result to the caller
+                pi, ps, pb, pev = pending
+                pev.synchronize()
+                if on_result is not None:
+                    on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(ev_c)
+                self.out_c[s][:b].copy_(out.cluster_map, non_blocking=True)
+                self.out_m[s][:b].copy_(out.road_mask, non_blocking=True)
+                ev_d = torch.cuda.Event()
+                ev_d.record(self.copy)
+            out.cluster_map.record_stream(self.copy)
+            out.road_mask.record_stream(self.copy)
+            self.d2h_bytes += 2 * b * H * W
+            pending = (i, s, b, ev_d)
+            up = nxt
+        pi, ps, pb, pev = pending
+        pev.synchronize()
+        if on_result is not None:
+            on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])

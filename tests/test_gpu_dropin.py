@@ -160,3 +160,25 @@ def test_product_has_no_cpu_fallback():
     from superpixel_align_b200 import _lib, ops
     with pytest.raises(_lib.SpalignError):
         ops.label_max(torch.zeros((1, 8, 8), dtype=torch.int32))   # CPU tensor
+
+
+def test_host_pipeline_streams_batches_and_matches_device_path():
+    from superpixel_align_b200 import ops, pipeline
+    d = torch.device('cuda', 0)
+    H, W, fh, fw, C = 128, 256, 16, 32, 32
+    labs = np.stack([synth.voronoi_labels(H, W, 6, 10, image_index=i) for i in range(5)])
+    feats = np.stack([synth.smooth_features(C, fh, fw, seed=i).reshape(C, -1).T for i in range(5)])
+    h_lab = torch.from_numpy(labs).pin_memory()
+    h_feat = torch.from_numpy(np.ascontiguousarray(feats)).pin_memory()
+    batches = [(h_lab[0:2], h_feat[0:2], [60, 60]), (h_lab[2:4], h_feat[2:4], [60, 60]),
+               (h_lab[4:5], h_feat[4:5], [60])]
+    got = {}
+    hp = pipeline.HostPipeline(H, W, fh, fw, C, sub_batch=2, k=4)
+    np.random.seed(7)
+    hp.process(batches, lambda i, c, m: got.__setitem__(i, (c.clone(), m.clone())))
+    assert sorted(got) == [0, 1, 2] and hp.h2d_bytes == labs.nbytes + feats.nbytes
+    np.random.seed(7)
+    for i, (l, f, n_sp) in enumerate(batches):
+        ref = pipeline.run_batch(l.to(d), f.to(d), n_sp, fh, fw, k=4)
+        assert torch.equal(ref.cluster_map.cpu(), got[i][0])
+        assert torch.equal(ref.road_mask.cpu(), got[i][1])
