@@ -155,6 +155,15 @@ int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, 
                          const int64_t* chunks, int n_chunks, const double* centers, int mode,
                          int32_t* assign, const int32_t* status, double* partials,
                          spalign_stream_t stream);
+/* sweep + reduce + update in ONE launch (single-GPU): the chunk of a group that finishes last
+ * (arrival ticket in counters[G], zero on entry and on exit) sums the group's partials in
+ * chunk order and applies the update, so the result is bit-identical to the three-call form. */
+int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                           int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
+                           const int64_t* chunks, int n_chunks, const int32_t* group_chunk_off,
+                           int mode, int n_iter, int32_t* assign, double* partials,
+                           double* totals, double* centers, int32_t* iters, int32_t* status,
+                           int32_t* counters, spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

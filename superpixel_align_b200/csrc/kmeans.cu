@@ -63,13 +63,12 @@ struct KmSmem {
   float* cen32;     // [K][Dc] centres rounded to fp32 (screening pass)
   char* part;       // [KM_THREADS][KMAX] partial distances (float or double)
   double* red;      // [8][KMAX] block reduction scratch of the exact pass
-  double* om;       // [TR] omega by sorted position
+  double* om;       // [8 warps][32] omega by sorted position (per-warp copy)
   double* extra;    // [KMAX][4] sum(omega), count, sum(omega*px), sum(omega*py)
   float* cnorm;     // [KMAX] upper bound of ||c_k||
-  int* order;       // [TR]
+  int* order;       // [8 warps][32] tile rows grouped by cluster (per-warp copy)
   int* anew;        // [TR] new assignment per tile row (-1: undecided)
   int* amb;         // [TR] tile rows that need the exact float64 pass
-  int* start;       // [KMAX+1]
   int* namb;        // [1]
   int* changed;     // [1]
 };
@@ -92,19 +91,17 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   if (s) s->red = reinterpret_cast<double*>(base + o);
   o += (size_t)8 * KMAX * sizeof(double);
   if (s) s->om = reinterpret_cast<double*>(base + o);
-  o += (size_t)32 * sizeof(double);
+  o += (size_t)8 * 32 * sizeof(double);
   if (s) s->extra = reinterpret_cast<double*>(base + o);
   o += (size_t)KMAX * 4 * sizeof(double);
   if (s) s->cnorm = reinterpret_cast<float*>(base + o);
   o += KMAX * sizeof(float);
   if (s) s->order = reinterpret_cast<int*>(base + o);
-  o += 32 * sizeof(int);
+  o += 8 * 32 * sizeof(int);
   if (s) s->anew = reinterpret_cast<int*>(base + o);
   o += 32 * sizeof(int);
   if (s) s->amb = reinterpret_cast<int*>(base + o);
   o += 32 * sizeof(int);
-  if (s) s->start = reinterpret_cast<int*>(base + o);
-  o += (KMAX + 1) * sizeof(int);
   if (s) s->namb = reinterpret_cast<int*>(base + o);
   o += sizeof(int);
   if (s) s->changed = reinterpret_cast<int*>(base + o);
@@ -184,26 +181,27 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     issue_tile<XT>(a, s.buf0, row_begin, (int)min((int64_t)TR, N));
     cp_async_commit();
   }
+  const int lane_ = t & 31, wq_ = t >> 5;
+  int* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
+  double* my_om = s.om + wq_ * 32;
   for (int ti = 0; ti < ntiles; ++ti) {
     const int64_t trow0 = row_begin + (int64_t)ti * TR;
     const int nvalid = (int)min((int64_t)TR, row_end - trow0);
-    if (ti + 1 < ntiles) {
+    cp_async_wait<0>();                    // this thread's copies of tile ti have landed
+    if (t == 0) *s.namb = 0;
+    // every warp keeps the old assignment / prior weight of tile row `lane` (L2 hits)
+    int pre_a = -1;
+    double pre_w = 0.0;
+    if (lane_ < nvalid) {
+      pre_a = assign[trow0 + lane_];
+      if (mode == 1) pre_w = a.w[trow0 + lane_];
+    }
+    __syncthreads();  // (A) tile ti visible; all warps are past phase 2 of tile ti-1
+    if (ti + 1 < ntiles) {  // prefetch the next tile into the buffer phase 2 just released
       issue_tile<XT>(a, s.buf0 + (size_t)((ti + 1) & 1) * s.tile_bytes, trow0 + TR,
                      (int)min((int64_t)TR, row_end - (trow0 + TR)));
       cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    if (t == 0) *s.namb = 0;
-    // warp 0 prefetches the old assignment and prior weight of its tile row (used in combine B)
-    int pre_a = -1;
-    double pre_w = 0.0;
-    if (t < 32 && t < nvalid && t < TR) {
-      pre_a = assign[trow0 + t];
-      if (mode == 1) pre_w = a.w[trow0 + t];
-    }
-    __syncthreads();
     const char* tile = s.buf0 + (size_t)(ti & 1) * s.tile_bytes;
 
     if (mode == 1) {
@@ -420,24 +418,22 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       }
     }
 
-    // ---- combine B: adopt the new assignment, omega, stable grouping by cluster ----
-    if (t < 32) {
-      const int lane = t;
-      const bool valid = lane < nvalid && lane < TR;
+    // ---- grouping (every warp, no block barrier): new assignment, omega, stable grouping of
+    // the tile's rows by cluster into per-warp shared-memory lists ----
+    int startk[KT + 1];
+    {
+      const int lane = lane_;
+      const bool valid = lane < nvalid;
       int a_new = -1;
       double om = 0.0;
       int chg = 0;
       if (valid) {
-        const int64_t grow = trow0 + lane;
-        const int a_old = pre_a;
         if (mode == 1) {
           a_new = s.anew[lane];
-          chg = a_new != a_old;
-          if (chg) assign[grow] = a_new;
-          const double wv = pre_w;
-          om = a_new == 0 ? wv : 1.0 - wv;
+          chg = a_new != pre_a;
+          om = a_new == 0 ? pre_w : 1.0 - pre_w;
         } else {
-          a_new = a_old;
+          a_new = pre_a;
           om = 1.0;
         }
       }
@@ -445,37 +441,42 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
+        startk[k] = base;
         if (k < K) {
           const unsigned m = __ballot_sync(0xffffffffu, valid && a_new == k);
           if (valid && a_new == k) pos = base + __popc(m & lt);
-          if (lane == 0) s.start[k] = base;
           base += __popc(m);
         }
       }
-      if (lane == 0) s.start[K] = base;
+      startk[KT] = base;
       if (valid && a_new >= 0 && a_new < K) {
-        s.order[pos] = lane;
-        s.om[pos] = om;
+        my_order[pos] = lane;
+        my_om[pos] = om;
       }
       const unsigned cm = __ballot_sync(0xffffffffu, chg != 0);
-      if (lane == 0 && cm) *s.changed += __popc(cm);
       __syncwarp();
-      if (lane < K) {  // lane k: per-cluster scalars, rows in order
-        const int i1 = s.start[lane + 1];
-        for (int i = s.start[lane]; i < i1; ++i) {
-          const double o = s.om[i];
-          e_w += o;
-          e_n += 1.0;
-          if (a.pos_mode) {
-            double px, py;
-            virtual_pos(a, trow0 + s.order[i], &px, &py);
-            e_x = fma(o, px, e_x);
-            e_y = fma(o, py, e_y);
+      if (wq_ == 0) {  // warp 0 owns the side effects
+        if (chg) assign[trow0 + lane] = a_new;
+        if (lane == 0 && cm) *s.changed += __popc(cm);
+        if (lane < K) {  // lane k: per-cluster scalars, rows in order
+          int i0 = 0, i1 = 0;
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+            if (k == lane) { i0 = startk[k]; i1 = startk[k + 1]; }
+          for (int i = i0; i < i1; ++i) {
+            const double o = my_om[i];
+            e_w += o;
+            e_n += 1.0;
+            if (a.pos_mode) {
+              double px, py;
+              virtual_pos(a, trow0 + my_order[i], &px, &py);
+              e_x = fma(o, px, e_x);
+              e_y = fma(o, py, e_y);
+            }
           }
         }
       }
     }
-    __syncthreads();
 
     // ---- phase 2: centroid sums, cluster by cluster, rows in order ----
 #pragma unroll
@@ -485,11 +486,11 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           if (k < K) {
-            const int i1 = s.start[k + 1];
+            const int i1 = startk[k + 1];
 #pragma unroll 4
-            for (int i = s.start[k]; i < i1; ++i) {
-              const double om = s.om[i];
-              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
+            for (int i = startk[k]; i < i1; ++i) {
+              const double om = my_om[i];
+              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)my_order[i] * a.srow);
               double x0, x1;
               if (kF32) {
                 const float2 v = *reinterpret_cast<const float2*>(xr + c0);
@@ -509,17 +510,17 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           if (k < K) {
-            const int i1 = s.start[k + 1];
-            for (int i = s.start[k]; i < i1; ++i) {
-              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)s.order[i] * a.srow);
-              acc[k][sl][0] = fma(s.om[i], (double)xr[c0], acc[k][sl][0]);
+            const int i1 = startk[k + 1];
+            for (int i = startk[k]; i < i1; ++i) {
+              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)my_order[i] * a.srow);
+              acc[k][sl][0] = fma(my_om[i], (double)xr[c0], acc[k][sl][0]);
             }
           }
         }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (t < K) {
     s.extra[t * 4 + 0] = e_w;
     s.extra[t * 4 + 1] = e_n;
@@ -661,7 +662,46 @@ struct SweepArgs {
   int32_t* assign;
   const int32_t* status;
   double* partials;       // [n_chunks][K*(D+2)+1]
+  // fused finish (optional): the last chunk of a group to finish reduces and updates
+  const int32_t* gco;     // [G+1] chunk offsets per group
+  int32_t* counters;      // [G] arrival tickets, zero between launches; NULL = no fused finish
+  double* totals;         // [G][K*(D+2)+1]
+  double* centers_rw;     // [G][K][D]
+  int32_t* iters;
+  int32_t* status_rw;
+  int n_iter;
 };
+
+// centres / stop flags of one group from its reduced totals (shared by kmeans_update_kernel
+// and the fused finish of kmeans_sweep_kernel); whole block, uniform control flow
+__device__ __forceinline__ void km_update_group(const double* tt, int D, int K, int mode,
+                                                int n_iter, double* c, int32_t* iters,
+                                                int32_t* status, int grp) {
+  const int pv = K * (D + 2) + 1;
+  const int t = threadIdx.x;
+  __shared__ int s_stop;
+  if (t == 0) s_stop = (mode == 1 && tt[pv - 1] == 0.0) ? 1 : 0;
+  __syncthreads();
+  if (s_stop) {  // assignment unchanged: centres stay (batch_spalign_kmeans.py:158-159)
+    if (t == 0) {
+      iters[grp] += 1;
+      status[grp] = SPALIGN_KM_CONVERGED;
+    }
+    return;
+  }
+  for (int i = t; i < K * D; i += blockDim.x) {
+    const int k = i / D, d = i - k * D;
+    c[i] = tt[(size_t)k * (D + 2) + d] / tt[(size_t)k * (D + 2) + D];
+  }
+  if (t == 0 && mode == 1) {
+    const int it = iters[grp] + 1;
+    iters[grp] = it;
+    bool empty = false;
+    for (int k = 0; k < K; ++k) empty |= (tt[(size_t)k * (D + 2) + D + 1] == 0.0);
+    if (empty) status[grp] = SPALIGN_KM_EMPTY_CLUSTER;
+    else if (it >= n_iter) status[grp] = SPALIGN_KM_ITER_CAP;
+  }
+}
 
 template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArgs g) {
@@ -709,6 +749,32 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
     out[(size_t)t * (D + 2) + D + 1] = s.extra[t * 4 + 1];
   }
   if (t == 0) out[pv - 1] = (double)*s.changed;
+  if (g.counters != nullptr) {
+    // fused finish: the chunk that arrives last sums the group's partials in chunk order
+    // (same order as kmeans_reduce_kernel -> same bits) and applies the update
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      const int nch = g.gco[grp + 1] - g.gco[grp];
+      s_last = atomicAdd(&g.counters[grp], 1) == nch - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      double* tt = g.totals + (size_t)grp * pv;
+      const int c0 = g.gco[grp], c1 = g.gco[grp + 1];
+      for (int j = t; j < (int)pv; j += KM_THREADS) {
+        double sum = 0.0;
+        for (int c = c0; c < c1; ++c) sum += __ldcg(g.partials + (size_t)c * pv + j);
+        tt[j] = sum;
+      }
+      __syncthreads();
+      km_update_group(tt, D, K, g.mode, g.n_iter, g.centers_rw + (size_t)grp * K * D, g.iters,
+                      g.status_rw, grp);
+      if (t == 0) g.counters[grp] = 0;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -728,31 +794,8 @@ kmeans_update_kernel(const double* __restrict__ totals, int D, int K, int mode, 
   const int grp = blockIdx.x;
   if (status[grp] != SPALIGN_KM_RUNNING) return;
   const int pv = K * (D + 2) + 1;
-  const double* tt = totals + (size_t)grp * pv;
-  const int t = threadIdx.x;
-  __shared__ int s_stop;
-  if (t == 0) s_stop = (mode == 1 && tt[pv - 1] == 0.0) ? 1 : 0;
-  __syncthreads();
-  if (s_stop) {  // assignment unchanged: centres stay (batch_spalign_kmeans.py:158-159)
-    if (t == 0) {
-      iters[grp] += 1;
-      status[grp] = SPALIGN_KM_CONVERGED;
-    }
-    return;
-  }
-  double* c = centers + (size_t)grp * K * D;
-  for (int i = t; i < K * D; i += 256) {
-    const int k = i / D, d = i - k * D;
-    c[i] = tt[(size_t)k * (D + 2) + d] / tt[(size_t)k * (D + 2) + D];
-  }
-  if (t == 0 && mode == 1) {
-    const int it = iters[grp] + 1;
-    iters[grp] = it;
-    bool empty = false;
-    for (int k = 0; k < K; ++k) empty |= (tt[(size_t)k * (D + 2) + D + 1] == 0.0);
-    if (empty) status[grp] = SPALIGN_KM_EMPTY_CLUSTER;
-    else if (it >= n_iter) status[grp] = SPALIGN_KM_ITER_CAP;
-  }
+  km_update_group(totals + (size_t)grp * pv, D, K, mode, n_iter, centers + (size_t)grp * K * D,
+                  iters, status, grp);
 }
 
 // seeded init for small groups: upper median by bitonic sort in shared memory
@@ -983,8 +1026,39 @@ extern "C" int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int
   if (rc) return rc;
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
+  g.gco = nullptr; g.counters = nullptr; g.totals = nullptr; g.centers_rw = nullptr;
+  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_sweep");
+}
+
+extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode,
+                                      int pos_w, int64_t pos_period, int64_t pos_row0,
+                                      const double* w, int D, int K, const int64_t* chunks,
+                                      int n_chunks, const int32_t* group_chunk_off, int mode,
+                                      int n_iter, int32_t* assign, double* partials,
+                                      double* totals, double* centers, int32_t* iters,
+                                      int32_t* status, int32_t* counters,
+                                      spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(chunks && group_chunk_off && assign && partials && totals && centers && iters &&
+                      status && counters && n_chunks > 0 && (mode == 0 || mode == 1),
+                  "kmeans_iterate: bad arguments");
+  Plan plan;
+  const int Dr = D - (pos_mode ? 2 : 0);
+  if (!make_plan(x_dtype, D, Dr, K, &plan)) {
+    set_error("kmeans_iterate: D=%d does not fit shared memory", D);
+    return SPALIGN_E_UNSUPPORTED;
+  }
+  SweepArgs g;
+  int rc = fill_args(&g.a, plan, X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K);
+  if (rc) return rc;
+  g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
+  g.partials = partials;
+  g.gco = group_chunk_off; g.counters = counters; g.totals = totals; g.centers_rw = centers;
+  g.iters = iters; g.status_rw = status; g.n_iter = n_iter;
+  KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
+  return check_launch("kmeans_iterate");
 }
 
 extern "C" int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off,

@@ -476,3 +476,21 @@ def test_kmeans_exact_ties_and_near_ties_take_first_minimum(ops):
         km.step()
         assert np.array_equal(km.assign.cpu().numpy(), want)
         assert km.iters[0].item() == 1
+
+
+def test_kmeans_fused_iterate_equals_three_kernel_path(ops):
+    rs = np.random.RandomState(21)
+    sizes = [900, 1000, 64, 2500]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = _blobs(rs, off[-1], 514, 4)
+    X[:, -2] = rs.uniform(0, 1023, len(X)); X[:, -1] = rs.uniform(0, 2047, len(X))
+    w = rs.uniform(0, 1, len(X))
+    init = np.concatenate([so.kmeans_init(4, w[a:b], rng=rs) for a, b in zip(off[:-1], off[1:])]).astype(np.int32)
+    args = (torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()), torch.from_numpy(init).to(dev()), 4, off)
+    a = ops.KMeansLarge(*args, fused=True).run()
+    b = ops.KMeansLarge(*args, fused=False).run(poll=3)
+    assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
+    assert torch.equal(a.status, b.status) and torch.equal(a.centers, b.centers)   # bit-identical
+    for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        want = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64), verbose=False)
+        assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
