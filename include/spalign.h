@@ -142,8 +142,10 @@ int spalign_kmeans_groups(const void* X, int x_dtype, int64_t ldx, int pos_mode,
                           spalign_stream_t stream);
 
 /* multi-CTA building blocks for large groups and for the multi-GPU global clustering:
- *   chunks [n_chunks,3] int64 device: (group, row_begin, row_end), sorted by group
- *   group_chunk_off [G+1] int32 device
+ *   chunks [n_chunks,4] int64 device, in launch order: (group, row_begin, row_end, slot);
+ *            slot = position of the chunk in `partials`; the slots of a group are contiguous
+ *            and ordered by row_begin
+ *   group_chunk_off [G+1] int32 device: slot range of every group
  *   partials [n_chunks, K*(D+2)+1] float64: per chunk and cluster k the D sums of omega*x,
  *            then sum(omega) and the member count ([K][D+2]); last element = #rows changed
  *   totals   [G, K*(D+2)+1] float64: fixed-order sum over the group's chunks

@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
 
 struct SweepArgs {
   KmArgs a;
-  const int64_t* chunks;  // [n_chunks][3]
+  const int64_t* chunks;  // [n_chunks][4]: group, row_begin, row_end, slot
   const double* centers;  // [G][K][D]
   int mode;
   int32_t* assign;
@@ -708,9 +708,11 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
   km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
-  const int ck = blockIdx.x;
-  const int grp = (int)g.chunks[(size_t)ck * 3];
-  const int64_t rb = g.chunks[(size_t)ck * 3 + 1], re = g.chunks[(size_t)ck * 3 + 2];
+  // chunks are listed in launch order (large ones first); column 3 is the chunk's slot in the
+  // group-contiguous, row-ordered partials array that the reduction walks
+  const int grp = (int)g.chunks[(size_t)blockIdx.x * 4];
+  const int64_t rb = g.chunks[(size_t)blockIdx.x * 4 + 1], re = g.chunks[(size_t)blockIdx.x * 4 + 2];
+  const int ck = (int)g.chunks[(size_t)blockIdx.x * 4 + 3];
   if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int t = threadIdx.x;
   const int K = g.a.K, D = g.a.D, Dr = g.a.Dr;
@@ -766,7 +768,15 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
       const int c0 = g.gco[grp], c1 = g.gco[grp + 1];
       for (int j = t; j < (int)pv; j += KM_THREADS) {
         double sum = 0.0;
-        for (int c = c0; c < c1; ++c) sum += __ldcg(g.partials + (size_t)c * pv + j);
+        int c = c0;
+        for (; c + 8 <= c1; c += 8) {  // 8 loads in flight, added in chunk order
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcg(g.partials + (size_t)(c + u) * pv + j);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sum += v[u];
+        }
+        for (; c < c1; ++c) sum += __ldcg(g.partials + (size_t)c * pv + j);
         tt[j] = sum;
       }
       __syncthreads();
@@ -784,7 +794,16 @@ kmeans_reduce_kernel(const double* __restrict__ partials, const int32_t* __restr
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= pv) return;
   double sum = 0.0;
-  for (int c = gco[grp]; c < gco[grp + 1]; ++c) sum += partials[(size_t)c * pv + j];
+  int c = gco[grp];
+  const int c1 = gco[grp + 1];
+  for (; c + 8 <= c1; c += 8) {  // 8 loads in flight, added in chunk order
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = partials[(size_t)(c + u) * pv + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += v[u];
+  }
+  for (; c < c1; ++c) sum += partials[(size_t)c * pv + j];
   totals[(size_t)grp * pv + j] = sum;
 }
 

@@ -354,18 +354,31 @@ class KMeansLarge:
         if self.chunks_per_group:
             per = np.maximum(1, -(-n // self.chunks_per_group))
             per = -(-per // self.TILE) * self.TILE
+            nch = np.maximum(1, -(-n // per))
+            rep = np.repeat(np.arange(len(active)), nch)
+            j = np.arange(int(nch.sum())) - np.repeat(np.cumsum(nch) - nch, nch)
+            rb = r0[rep] + j * per[rep]
+            re = np.minimum(rb + per[rep], r1[rep])
+            size_rank = np.zeros(len(rb), dtype=np.int64)
         else:
+            # uniform chunks; per-CTA fixed cost (centres, screening set-up, partials) argues
+            # for large chunks, load balance for small ones: 32..256 rows by active volume
             total = int(n.sum())
             rpc = max(2 * self.TILE, min(16 * self.TILE, total // self.TARGET_CHUNKS))
             rpc = -(-rpc // self.TILE) * self.TILE
             per = np.full(len(active), rpc, dtype=np.int64)
-        nch = np.maximum(1, -(-n // per))
+            nch = np.maximum(1, -(-n // per))
+            rep = np.repeat(np.arange(len(active)), nch)
+            j = np.arange(int(nch.sum())) - np.repeat(np.cumsum(nch) - nch, nch)
+            rb = r0[rep] + j * per[rep]
+            re = np.minimum(rb + per[rep], r1[rep])
+            size_rank = np.zeros(len(rb), dtype=np.int64)
         tot = int(nch.sum())
-        rep = np.repeat(np.arange(len(active)), nch)
-        j = np.arange(tot) - np.repeat(np.cumsum(nch) - nch, nch)
-        rb = r0[rep] + j * per[rep]
-        re = np.minimum(rb + per[rep], r1[rep])
-        chunks = np.stack([active[rep], rb, np.maximum(re, rb)], axis=1).astype(np.int64)
+        # slot = group-contiguous, row-ordered position (what the fixed-order reduction walks);
+        # launch order = large chunks first (stable)
+        slot = np.arange(tot, dtype=np.int64)
+        order = np.argsort(size_rank, kind='stable')
+        chunks = np.stack([active[rep], rb, np.maximum(re, rb), slot], axis=1).astype(np.int64)[order]
         counts = np.zeros(self.G, dtype=np.int64)
         counts[active] = nch
         gco = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
