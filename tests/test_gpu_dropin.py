@@ -182,3 +182,25 @@ def test_host_pipeline_streams_batches_and_matches_device_path():
         ref = pipeline.run_batch(l.to(d), f.to(d), n_sp, fh, fw, k=4)
         assert torch.equal(ref.cluster_map.cpu(), got[i][0])
         assert torch.equal(ref.road_mask.cpu(), got[i][1])
+
+
+def test_results_scores_and_artefacts(tmp_path):
+    from superpixel_align_b200 import results
+    rs = np.random.RandomState(1)
+    cityscapes = rs.randint(0, 12, size=(2, 40, 60)).astype(np.uint8)
+    gt = np.stack([results.create_label_mask(c) for c in cityscapes])
+    assert set(np.unique(gt)) == {-1, 0, 1}
+    road = rs.rand(2, 40, 60) < 0.4
+    scores = results.road_scores(road, gt)
+    for i in range(2):
+        iou, prec, rec, tp, fp, fn = so.road_iou(road[i], gt[i])
+        assert (scores[i]['TP'], scores[i]['FP'], scores[i]['FN']) == (tp, fp, fn)
+        assert scores[i]['road_iou'] == pytest.approx(iou) and scores[i]['precision'] == pytest.approx(prec)
+    args = types.SimpleNamespace(n_clusters=4, batchsize=30)
+    info = results.save_info(str(tmp_path), 'a/b/frankfurt_000000_000294_leftImg8bit.png', 'lab.png',
+                             road[0], road[0].astype(np.int64) * 2, scores[0], args, {'time_kmeans': 0.1}, None)
+    assert np.array_equal(np.load(tmp_path / 'frankfurt_000000_000294_leftImg8bit.npy'), road[0].astype(np.uint8))
+    assert np.load(tmp_path / 'frankfurt_000000_000294_leftImg8bit_all_cluster.npy').dtype == np.uint8
+    import json
+    rec = json.loads(open(tmp_path / 'result.json').read().strip())
+    assert rec['road_iou'] == info['road_iou'] and rec['n_clusters'] == 4 and rec['time_kmeans'] == 0.1
