@@ -110,6 +110,34 @@ int spalign_pool(const float* feat, int n_img, int C, int fh, int fw, const int6
                  const int64_t* sum_y, const int64_t* sum_x, int append_pos, float* out,
                  int64_t ld_out, spalign_stream_t stream);
 
+/* Same SpMM with float64 weights (bilinear overlap matrix, below). */
+int spalign_pool_weighted(const float* feat, int n_img, int C, int fh, int fw,
+                          const int64_t* sp_off, int64_t n_rows, int max_rows_per_image,
+                          const int32_t* indptr, const int32_t* indices, const double* wvals,
+                          const int32_t* area, const int64_t* sum_y, const int64_t* sum_x,
+                          int append_pos, float* out, int64_t ld_out, spalign_stream_t stream);
+
+/* ---- K1b: bilinear-weight overlap matrix ----------------------------------
+ * Dense superpixel pooling of notebooks/Superpixel_Align.ipynb cell 4 (resize the feature
+ * map to the image size with chainer.functions.resize_images, mean over each superpixel) as a
+ * sparse matrix: W[r, c] = sum over the pixels p of superpixel r of the bilinear weight of
+ * cell c at p (corner-aligned sampling u = linspace(0, n_in-1, n_out), lower neighbour
+ * clip(floor(u), 0, n_in-2)).  The per-axis tables are computed by the caller (host, float64):
+ *   iy0[H] lower neighbour row, wy0[H]/wy1[H] its weight and the upper neighbour's,
+ *   ystart[fh+1] first y with iy0[y] >= cy; ix0, wx0, wx1, xstart likewise.
+ * Output: CSR with ascending columns, float64 weights wvals[nnz_cap]; row_weight[n_rows]
+ * (optional) = sum of a row's weights (= superpixel area up to rounding).  Bit-reproducible. */
+size_t spalign_overlap_bilinear_workspace_bytes(int n_img, int H, int W, int fh, int fw,
+                                                int64_t n_rows, int64_t nnz_cap);
+int spalign_overlap_bilinear_csr(const void* labels, int label_dtype, int n_img, int H, int W,
+                                 int fh, int fw, const int64_t* sp_off, int64_t n_rows,
+                                 const int32_t* iy0, const double* wy0, const double* wy1,
+                                 const int32_t* ystart, const int32_t* ix0, const double* wx0,
+                                 const double* wx1, const int32_t* xstart, int64_t nnz_cap,
+                                 int32_t* indptr, int32_t* indices, double* wvals,
+                                 double* row_weight, int64_t* nnz_flags, void* workspace,
+                                 size_t ws_bytes, spalign_stream_t stream);
+
 /* Layout helper: [n_img, C, ncell] (NCHW, what F.concat yields at batch_spalign_kmeans.py:435)
  * -> [n_img, ncell, C] cell-major.  direct_clustering.py:302 does the same transpose. */
 int spalign_nchw_to_cellmajor(const float* src, float* dst, int n_img, int C, int ncell,

@@ -385,3 +385,78 @@ def spalign_image_cpu(label, feat_cellmajor, fh, fw, k=4, prior=(0.75, 0.5, 0.1,
     return dict(indptr=indptr, indices=indices, counts=counts, area=area, sum_y=sy, sum_x=sx,
                 features=feat, weights=w, assign=assign, info=info, cluster_map=cmap[0],
                 road_mask=road[0])
+
+
+# --------------------------------------------------------------------------------------
+# f2. bilinear-weight overlap matrix (dense pooling of notebooks/Superpixel_Align.ipynb cell 4)
+# --------------------------------------------------------------------------------------
+# The notebook resizes the feature map to the image size with chainer.functions.resize_images
+# and takes the mean over each superpixel.  chainer (v3/v4, not in the tree: parity unpinned)
+# samples with corner alignment: u = linspace(0, n_in - 1, n_out), u0 = clip(floor(u), 0,
+# n_in - 2), u1 = u0 + 1, weights (u1 - u) and (u - u0).
+
+
+def bilinear_axis(n_out: int, n_in: int):
+    """(i0 [n_out] int, w0 [n_out], w1 [n_out]): output index o reads w0*in[i0] + w1*in[i0+1]."""
+    assert n_in >= 2, 'bilinear resize needs at least 2 input samples per axis'
+    u = np.linspace(0, n_in - 1, num=n_out)
+    i0 = np.clip(np.floor(u).astype(np.int64), 0, n_in - 2)
+    return i0, (i0 + 1) - u, u - i0
+
+
+def resize_bilinear(feature_map, H, W):
+    """[C, fh, fw] -> float64 [C, H, W], chainer F.resize_images semantics."""
+    F = np.asarray(feature_map, dtype=np.float64)
+    C, fh, fw = F.shape
+    v0, wv0, wv1 = bilinear_axis(H, fh)
+    u0, wu0, wu1 = bilinear_axis(W, fw)
+    rows = wv0[None, :, None] * F[:, v0, :] + wv1[None, :, None] * F[:, v0 + 1, :]   # [C, H, fw]
+    return wu0[None, None, :] * rows[:, :, u0] + wu1[None, None, :] * rows[:, :, u0 + 1]
+
+
+def pool_dense_bilinear(label, feature_map):
+    """Mean of the bilinearly resized map over each superpixel (notebook cell 4). Small inputs."""
+    label = np.asarray(label)
+    H, W = label.shape
+    up = resize_bilinear(feature_map, H, W)
+    S = int(label.max()) + 1
+    return np.stack([up[:, label == s].mean(axis=1) for s in range(S)])
+
+
+def overlap_bilinear_csr(label, fh, fw, n_sp=None):
+    """CSR of Wb[s, c] = sum over pixels p of superpixel s of the bilinear weight of cell c at p.
+    Every pixel contributes its four neighbours (zero weights included), columns ascending.
+    Returns (indptr int32, indices int32, wvals float64); row sums equal the superpixel areas."""
+    label = np.asarray(label)
+    H, W = label.shape
+    if n_sp is None:
+        n_sp = int(label.max()) + 1
+    v0, wv0, wv1 = bilinear_axis(H, fh)
+    u0, wu0, wu1 = bilinear_axis(W, fw)
+    nc = fh * fw
+    lab = label.astype(np.int64)
+    keys, vals = [], []
+    for dv, wv in ((0, wv0), (1, wv1)):
+        for du, wu in ((0, wu0), (1, wu1)):
+            cell = (v0[:, None] + dv) * fw + (u0[None, :] + du)
+            keys.append((lab * nc + cell).ravel())
+            vals.append((wv[:, None] * wu[None, :]).ravel())
+    keys = np.concatenate(keys)
+    vals = np.concatenate(vals)
+    uk, inv = np.unique(keys, return_inverse=True)
+    wsum = np.bincount(inv, weights=vals, minlength=len(uk))
+    rows = uk // nc
+    indptr = np.zeros(n_sp + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    return np.cumsum(indptr).astype(np.int32), (uk % nc).astype(np.int32), wsum
+
+
+def pool_weighted(indptr, indices, wvals, feat_cellmajor, area):
+    """feat[s] = sum_c W[s,c] * F[c] / area[s] (float64)."""
+    F = np.asarray(feat_cellmajor, dtype=np.float64)
+    S = len(indptr) - 1
+    out = np.zeros((S, F.shape[1]))
+    for s in range(S):
+        a, b = indptr[s], indptr[s + 1]
+        out[s] = np.asarray(wvals[a:b]) @ F[indices[a:b]]
+    return out / np.asarray(area, dtype=np.float64)[:, None]

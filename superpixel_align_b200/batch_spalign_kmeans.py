@@ -229,7 +229,10 @@ def kmeans(k, X, weights=None, n_iter=1000, init_assign=None):
     return res.assign
 
 
-def _features_for(st, feature_maps, dev, append_pos):
+POOLING = 'count'   # module default; 'bilinear' = dense resize+mean of the notebook (f2)
+
+
+def _features_for(st, feature_maps, dev, append_pos, pooling=None):
     fm = _unwrap(feature_maps)
     if isinstance(fm, (list, tuple)):
         fm = torch.stack([_to_dev(f, dev) for f in fm])
@@ -237,18 +240,23 @@ def _features_for(st, feature_maps, dev, append_pos):
     if fm.dim() == 3:
         fm = fm[None]
     cell = ops.as_cellmajor(fm)
+    if (pooling or POOLING) == 'bilinear':
+        bw = ops.overlap_bilinear_csr(st.labels, st.fh, st.fw, st.ov)
+        return ops.pool_weighted(cell, st.ov, bw, append_pos=append_pos)
     return ops.pool(cell, st.ov, append_pos=append_pos)
 
 
-def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, append_pos=False):
+def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, append_pos=False,
+                     pooling=None):
     """One descriptor per superpixel, [S, C(+2)] in sorted-label order
-    (batch_spalign_kmeans.py:210-276; count pooling, see module docstring)."""
+    (batch_spalign_kmeans.py:210-276; count pooling, see module docstring).
+    ``pooling='bilinear'`` = mean of the bilinearly resized map (Superpixel_Align.ipynb cell 4)."""
     fm = _unwrap(feature_map)
     as_numpy = not isinstance(fm, torch.Tensor)
     dev = _device() if as_numpy else fm.device
     fh, fw = fm.shape[-2:]
     st = _batch_state(superpixels, dev, fh, fw, None)
-    feat = _features_for(st, fm, dev, append_pos)
+    feat = _features_for(st, fm, dev, append_pos, pooling)
     if as_numpy:
         out = feat.cpu().numpy()
         return out.astype(np.float64) if append_pos else out  # reference dtypes (:270)
@@ -266,7 +274,7 @@ def batch_superpixel_align(args, model, imgs, superpixels, feature_maps):
     fh, fw = fm.shape[-2:]
     st = _batch_state(superpixels, dev, fh, fw, _prior_from_args(args))
     append_pos = not getattr(args, 'without_pos', False)
-    feat = _features_for(st, fm, dev, append_pos)
+    feat = _features_for(st, fm, dev, append_pos, getattr(args, 'spalign_pooling', None))
     n_per = [int(v) for v in st.n_sp]
     if as_numpy:
         out = feat.cpu().numpy()

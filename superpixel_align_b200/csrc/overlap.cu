@@ -347,6 +347,82 @@ emit_generic_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int
   flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
 }
 
+// Bilinear-weight pairs (dense pooling of notebooks/Superpixel_Align.ipynb cell 4):
+// W[s, c] = sum over the pixels p of superpixel s of the bilinear weight of cell c at p, with
+// the corner-aligned sampling of chainer.functions.resize_images.  One thread per cell walks
+// the cell's support window (the pixel rows/columns whose lower neighbour is cy-1 or cy) once
+// to find the next label and once to accumulate it, labels in ascending order; sums are
+// float64 in fixed row-major order.  `cnt` carries the number of contributing pixels.
+struct BilinearAxes {
+  const int* iy0;      // [H] lower neighbour row of pixel row y (0..fh-2)
+  const double* wy0;   // [H] weight of iy0[y]
+  const double* wy1;   // [H] weight of iy0[y] + 1
+  const int* ystart;   // [fh+1] first y with iy0[y] >= cy
+  const int* ix0;      // [W]
+  const double* wx0;
+  const double* wx1;
+  const int* xstart;   // [fw+1]
+};
+
+template <typename LabelT>
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_bilinear_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
+                     const int64_t* __restrict__ sp_off, BilinearAxes ax, int cap_img,
+                     OverlapWs ws, int64_t* sum_y, int64_t* sum_x, int64_t* nnz_flags) {
+  __shared__ PairStage st;
+  const int img = blockIdx.y;
+  const int ncell = fh * fw;
+  const int c = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  if (threadIdx.x == 0) st.count = 0;
+  __syncthreads();
+  const int64_t row0 = sp_off[img];
+  const long long n_sp = sp_off[img + 1] - row0;
+  if (c < ncell) {
+    const int cy = c / fw, cx = c - cy * fw;
+    const int y0 = ax.ystart[cy > 0 ? cy - 1 : 0], y1 = ax.ystart[cy + 1];
+    const int x0 = ax.xstart[cx > 0 ? cx - 1 : 0], x1 = ax.xstart[cx + 1];
+    const LabelT* base = labels + (size_t)img * H * W;
+    long long lo = -1;
+    bool bad = false;
+    while (true) {
+      long long cur = 0x7fffffffffffffffLL;
+      for (int y = y0; y < y1; ++y) {
+        const LabelT* rowp = base + (size_t)y * W;
+        for (int x = x0; x < x1; ++x) {
+          const long long q = (long long)rowp[x];
+          if (q < 0 || q >= n_sp) {
+            bad = true;
+          } else if (q > lo && q < cur) {
+            cur = q;
+          }
+        }
+      }
+      if (cur == 0x7fffffffffffffffLL) break;
+      int cnt = 0;
+      double acc = 0.0;
+      for (int y = y0; y < y1; ++y) {
+        const LabelT* rowp = base + (size_t)y * W;
+        const double hy = (ax.iy0[y] == cy) ? ax.wy0[y] : ax.wy1[y];
+        double ra = 0.0;
+        for (int x = x0; x < x1; ++x) {
+          if ((long long)rowp[x] == cur) {
+            ra = __dadd_rn(ra, (ax.ix0[x] == cx) ? ax.wx0[x] : ax.wx1[x]);
+            ++cnt;
+          }
+        }
+        acc = __fma_rn(hy, ra, acc);
+      }
+      stage_pair(st, ws, img, cap_img, (int)(row0 + cur), c, cnt, 0, 0, acc, sum_y, sum_x,
+                 nnz_flags);
+      lo = cur;
+    }
+    if (bad)
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_LABEL_RANGE);
+  }
+  flush_stage(st, ws, img, cap_img, sum_y, sum_x, nnz_flags);
+}
+
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int warp_incl_scan(int v) {
 #pragma unroll
@@ -482,7 +558,7 @@ scatter_kernel(OverlapWs ws, int cap_img, const int* __restrict__ indptr, int64_
 // one warp per row with <= WARP_TIER_MAX cells: rank sort by cell id
 __global__ void __launch_bounds__(256)
 rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int* indices,
-                    int* counts, int* area, double* sum_prior,
+                    int* counts, int* area, double* sum_prior, double* wvals,
                     const int64_t* __restrict__ nnz_flags) {
   if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
@@ -508,9 +584,11 @@ rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int
     }
     if (valid) {
       const int cn = ws.u_cnt[base + e];
+      const double pv = ws.u_prior[base + e];
       indices[base + rank] = myc;
       counts[base + rank] = cn;
-      sorted_prior[base + rank] = ws.u_prior[base + e];
+      sorted_prior[base + rank] = pv;
+      if (wvals != nullptr) wvals[base + rank] = pv;
       a_sum += cn;
     }
   }
@@ -530,7 +608,7 @@ rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int
 // rows longer than WARP_TIER_MAX: scatter into a dense per-cell array, compact in order
 __global__ void __launch_bounds__(HEAVY_THREADS)
 rowsort_heavy_kernel(OverlapWs ws, const int* __restrict__ indptr, int ncell, int* indices,
-                     int* counts, int* area, double* sum_prior,
+                     int* counts, int* area, double* sum_prior, double* wvals,
                      const int64_t* __restrict__ nnz_flags) {
   if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
   const int n_heavy = min(*ws.heavy_count, ws.heavy_cap);
@@ -562,6 +640,7 @@ rowsort_heavy_kernel(OverlapWs ws, const int* __restrict__ indptr, int ncell, in
       if (flag) {
         indices[base + running + excl] = c;
         counts[base + running + excl] = cn;
+        if (wvals != nullptr) wvals[base + running + excl] = d_prior[c];
         a_sum += cn;
         p_sum = __dadd_rn(p_sum, d_prior[c]);
       }
@@ -705,9 +784,81 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
   rowsort_warp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
-      ws, indptr, n_rows, indices, counts, area, sum_prior, nnz_flags);
+      ws, indptr, n_rows, indices, counts, area, sum_prior, nullptr, nnz_flags);
   rowsort_heavy_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(ws, indptr, ncell, indices,
                                                                  counts, area, sum_prior,
-                                                                 nnz_flags);
+                                                                 nullptr, nnz_flags);
   return check_launch("overlap_csr");
+}
+
+extern "C" size_t spalign_overlap_bilinear_workspace_bytes(int n_img, int H, int W, int fh, int fw,
+                                                           int64_t n_rows, int64_t nnz_cap) {
+  (void)H;
+  (void)W;
+  OverlapWs ws;
+  // + counts[cap], area[R], sum_y[R], sum_x[R], sum_prior[R] scratch that the caller does not see
+  return carve(ws, nullptr, n_img, fh * fw, n_rows, nnz_cap) + (size_t)nnz_cap * 4 +
+         (size_t)n_rows * (4 + 8 + 8 + 8) + 6 * 256;
+}
+
+extern "C" int spalign_overlap_bilinear_csr(
+    const void* labels, int label_dtype, int n_img, int H, int W, int fh, int fw,
+    const int64_t* sp_off, int64_t n_rows, const int32_t* iy0, const double* wy0,
+    const double* wy1, const int32_t* ystart, const int32_t* ix0, const double* wx0,
+    const double* wx1, const int32_t* xstart, int64_t nnz_cap, int32_t* indptr, int32_t* indices,
+    double* wvals, double* row_weight, int64_t* nnz_flags, void* workspace, size_t ws_bytes,
+    spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(labels && sp_off && iy0 && wy0 && wy1 && ystart && ix0 && wx0 && wx1 && xstart &&
+                      indptr && indices && wvals && nnz_flags && workspace,
+                  "overlap_bilinear_csr: NULL argument");
+  SPALIGN_REQUIRE(n_img > 0 && H > 0 && W > 0 && fh >= 2 && fw >= 2 && n_rows > 0,
+                  "overlap_bilinear_csr: bad shape (fh, fw must be >= 2)");
+  SPALIGN_REQUIRE(label_dtype == SPALIGN_I32 || label_dtype == SPALIGN_I64,
+                  "overlap_bilinear_csr: label_dtype must be I32 or I64");
+  SPALIGN_REQUIRE(n_rows < 0x7fffffffLL && nnz_cap > 0 && nnz_cap < 0x7fffffffLL,
+                  "overlap_bilinear_csr: n_rows / nnz_cap must fit int32");
+  const int cap_img = (int)(nnz_cap / n_img);
+  SPALIGN_REQUIRE(cap_img > 0, "overlap_bilinear_csr: nnz_cap smaller than n_img");
+  const int ncell = fh * fw;
+  size_t need = spalign_overlap_bilinear_workspace_bytes(n_img, H, W, fh, fw, n_rows, nnz_cap);
+  if (ws_bytes < need) {
+    set_error("overlap_bilinear_csr: workspace %zu < %zu bytes", ws_bytes, need);
+    return SPALIGN_E_WORKSPACE;
+  }
+  void* aligned = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  OverlapWs ws;
+  size_t used = carve(ws, aligned, n_img, ncell, n_rows, nnz_cap);
+  Carver extra(static_cast<char*>(aligned) + used);
+  int* counts = extra.take<int>(nnz_cap);
+  int* area = extra.take<int>(n_rows);
+  int64_t* sum_y = extra.take<int64_t>(n_rows);
+  int64_t* sum_x = extra.take<int64_t>(n_rows);
+  double* sum_prior = row_weight ? row_weight : extra.take<double>(n_rows);
+
+  init_kernel<<<2 * kNumSMs, 256, 0, stream>>>(ws.zero_begin, ws.zero_ints, sum_y, sum_x, n_rows,
+                                               nnz_flags);
+  BilinearAxes ax{iy0, wy0, wy1, ystart, ix0, wx0, wx1, xstart};
+  dim3 egrid((ncell + EMIT_THREADS - 1) / EMIT_THREADS, n_img);
+  if (label_dtype == SPALIGN_I32)
+    emit_bilinear_kernel<int32_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+        (const int32_t*)labels, H, W, fh, fw, sp_off, ax, cap_img, ws, sum_y, sum_x, nnz_flags);
+  else
+    emit_bilinear_kernel<int64_t><<<egrid, EMIT_THREADS, 0, stream>>>(
+        (const int64_t*)labels, H, W, fh, fw, sp_off, ax, cap_img, ws, sum_y, sum_x, nnz_flags);
+  const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
+  scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum);
+  scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum, n_tiles,
+                                                  indptr, nnz_flags, nnz_cap, ws.heavy_rows,
+                                                  ws.heavy_count, ws.heavy_cap, ws.pair_count,
+                                                  n_img);
+  int sgx = (cap_img + 256 * 4 - 1) / (256 * 4);
+  sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
+  scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
+  rowsort_warp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
+      ws, indptr, n_rows, indices, counts, area, sum_prior, wvals, nnz_flags);
+  rowsort_heavy_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(ws, indptr, ncell, indices,
+                                                                 counts, area, sum_prior, wvals,
+                                                                 nnz_flags);
+  return check_launch("overlap_bilinear_csr");
 }

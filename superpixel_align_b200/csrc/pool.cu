@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256)
 pool_rows_kernel(const float* __restrict__ feat, int C, int ncell,
                  const int64_t* __restrict__ sp_off, const int32_t* __restrict__ indptr,
                  const int32_t* __restrict__ indices, const int32_t* __restrict__ counts,
-                 const int32_t* __restrict__ area, const int64_t* __restrict__ sum_y,
+                 const double* __restrict__ wvals, const int32_t* __restrict__ area, const int64_t* __restrict__ sum_y,
                  const int64_t* __restrict__ sum_x, int append_pos, float* __restrict__ out,
                  int64_t ld_out) {
   const int img = blockIdx.y;
@@ -68,7 +68,7 @@ pool_rows_kernel(const float* __restrict__ feat, int C, int ncell,
     __syncthreads();
     for (int e = t; e < n; e += blockDim.x) {
       s_idx[e] = indices[base + e0 + e];
-      s_cnt[e] = (float)counts[base + e0 + e];
+      s_cnt[e] = counts != nullptr ? (float)counts[base + e0 + e] : (float)wvals[base + e0 + e];
     }
     __syncthreads();
     int e = 0;
@@ -137,14 +137,13 @@ extern "C" int spalign_nchw_to_cellmajor(const float* src, float* dst, int n_img
   return check_launch("nchw_to_cellmajor");
 }
 
-extern "C" int spalign_pool(const float* feat, int n_img, int C, int fh, int fw,
-                            const int64_t* sp_off, int64_t n_rows, int max_rows_per_image,
-                            const int32_t* indptr, const int32_t* indices,
-                            const int32_t* counts, const int32_t* area, const int64_t* sum_y,
-                            const int64_t* sum_x, int append_pos, float* out, int64_t ld_out,
-                            spalign_stream_t stream_) {
+static int pool_impl(const float* feat, int n_img, int C, int fh, int fw, const int64_t* sp_off,
+                     int64_t n_rows, int max_rows_per_image, const int32_t* indptr,
+                     const int32_t* indices, const int32_t* counts, const double* wvals,
+                     const int32_t* area, const int64_t* sum_y, const int64_t* sum_x,
+                     int append_pos, float* out, int64_t ld_out, spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SPALIGN_REQUIRE(feat && sp_off && indptr && indices && counts && area && out,
+  SPALIGN_REQUIRE(feat && sp_off && indptr && indices && (counts || wvals) && area && out,
                   "pool: NULL argument");
   SPALIGN_REQUIRE(!append_pos || (sum_y && sum_x), "pool: append_pos needs sum_y/sum_x");
   SPALIGN_REQUIRE(n_img > 0 && n_img <= 65535 && fh > 0 && fw > 0 && n_rows > 0 &&
@@ -174,11 +173,34 @@ extern "C" int spalign_pool(const float* feat, int n_img, int C, int fh, int fw,
                   "pool: unsupported channel count %d", C);
 #define LAUNCH(N)                                                                              \
   pool_rows_kernel<N><<<grid, threads, 0, stream>>>(feat, C, ncell, sp_off, indptr, indices,   \
-                                                    counts, area, sum_y, sum_x, append_pos,    \
-                                                    out, ld_out)
+                                                    counts, wvals, area, sum_y, sum_x,         \
+                                                    append_pos, out, ld_out)
   if (nacc == 1) LAUNCH(1);
   else if (nacc == 2) LAUNCH(2);
   else LAUNCH(4);
 #undef LAUNCH
   return check_launch("pool");
+}
+
+extern "C" int spalign_pool(const float* feat, int n_img, int C, int fh, int fw,
+                            const int64_t* sp_off, int64_t n_rows, int max_rows_per_image,
+                            const int32_t* indptr, const int32_t* indices,
+                            const int32_t* counts, const int32_t* area, const int64_t* sum_y,
+                            const int64_t* sum_x, int append_pos, float* out, int64_t ld_out,
+                            spalign_stream_t stream) {
+  SPALIGN_REQUIRE(counts != nullptr, "pool: NULL counts");
+  return pool_impl(feat, n_img, C, fh, fw, sp_off, n_rows, max_rows_per_image, indptr, indices,
+                   counts, nullptr, area, sum_y, sum_x, append_pos, out, ld_out, stream);
+}
+
+extern "C" int spalign_pool_weighted(const float* feat, int n_img, int C, int fh, int fw,
+                                     const int64_t* sp_off, int64_t n_rows,
+                                     int max_rows_per_image, const int32_t* indptr,
+                                     const int32_t* indices, const double* wvals,
+                                     const int32_t* area, const int64_t* sum_y,
+                                     const int64_t* sum_x, int append_pos, float* out,
+                                     int64_t ld_out, spalign_stream_t stream) {
+  SPALIGN_REQUIRE(wvals != nullptr, "pool_weighted: NULL wvals");
+  return pool_impl(feat, n_img, C, fh, fw, sp_off, n_rows, max_rows_per_image, indptr, indices,
+                   nullptr, wvals, area, sum_y, sum_x, append_pos, out, ld_out, stream);
 }

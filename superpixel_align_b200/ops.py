@@ -19,7 +19,7 @@ from ._lib import check
 LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 
 # kernel launches per entry point (kept in sync with csrc/*.cu)
-_LAUNCH_COST = dict(label_max=1, overlap_csr=7, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
+_LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
                     kmeans_sweep=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
                     refine=2, confusion2=1)
 
@@ -189,6 +189,89 @@ def overlap_csr(labels: torch.Tensor, fh: int, fw: int, n_sp: Sequence[int],
                 raise OverflowError('overlap CSR capacity exceeded at the maximum capacity')
             return overlap_csr(labels, fh, fw, n_sp, prior, bigger, retry=True)
     return ov
+
+
+def bilinear_axis(n_out: int, n_in: int):
+    """Corner-aligned bilinear sampling tables of chainer.functions.resize_images along one
+    axis: (i0 int32 [n_out], w0, w1 float64 [n_out], start int32 [n_in+1]) with
+    out[o] = w0[o]*in[i0[o]] + w1[o]*in[i0[o]+1] and start[c] = first o with i0[o] >= c."""
+    assert n_in >= 2, 'bilinear pooling needs at least 2 feature cells per axis'
+    u = np.linspace(0, n_in - 1, num=n_out)
+    i0 = np.clip(np.floor(u).astype(np.int64), 0, n_in - 2)
+    start = np.searchsorted(i0, np.arange(n_in + 1), side='left').astype(np.int32)
+    return i0.astype(np.int32), (i0 + 1) - u, u - i0, start
+
+
+@dataclass
+class BilinearOverlap:
+    """CSR bilinear-weight overlap matrix of a batch (device tensors)."""
+    indptr: torch.Tensor       # int32 [n_rows+1]
+    indices: torch.Tensor      # int32 [nnz_cap]
+    wvals: torch.Tensor        # float64 [nnz_cap]
+    row_weight: torch.Tensor   # float64 [n_rows] (= area up to rounding)
+    nnz_flags: torch.Tensor    # int64 [4]
+
+    def validate(self):
+        nnz, flags, hw, _ = self.nnz_flags.tolist()
+        if flags & _lib.F_NNZ_OVERFLOW:
+            raise OverflowError('bilinear overlap CSR capacity exceeded (nnz=%d)' % nnz)
+        if flags & _lib.F_LABEL_RANGE:
+            raise ValueError('label map holds ids outside [0, n_superpixels)')
+        return nnz
+
+
+def overlap_bilinear_csr(labels: torch.Tensor, fh: int, fw: int, ov: Overlap,
+                         nnz_cap_per_image: Optional[int] = None) -> BilinearOverlap:
+    """K1b.  Bilinear-weight overlap matrix for the same batch / row numbering as ``ov``."""
+    _require_cuda(labels)
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    dev = labels.device
+    ncell = fh * fw
+    if nnz_cap_per_image is None:
+        nnz_cap_per_image = min(4 * H * W, 6 * ncell + 8 * ov.max_rows + 1024)
+    cap = int(nnz_cap_per_image) * n
+
+    def make():
+        iy0, wy0, wy1, ys = bilinear_axis(H, fh)
+        ix0, wx0, wx1, xs = bilinear_axis(W, fw)
+        return tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                     for a in (iy0, wy0, wy1, ys, ix0, wx0, wx1, xs))
+    tabs = _cached_const(('bilinear', dev, H, W, fh, fw), make)
+    lib = _lib.load()
+    ws_bytes = lib.spalign_overlap_bilinear_workspace_bytes(n, H, W, fh, fw, ov.n_rows, cap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    out = BilinearOverlap(
+        indptr=torch.empty(ov.n_rows + 1, dtype=torch.int32, device=dev),
+        indices=torch.empty(cap, dtype=torch.int32, device=dev),
+        wvals=torch.empty(cap, dtype=torch.float64, device=dev),
+        row_weight=torch.empty(ov.n_rows, dtype=torch.float64, device=dev),
+        nnz_flags=torch.empty(4, dtype=torch.int64, device=dev))
+    check(lib.spalign_overlap_bilinear_csr(
+        _ptr(labels), _label_code(labels), n, H, W, fh, fw, _ptr(ov.sp_off), ov.n_rows,
+        *[_ptr(t) for t in tabs], cap, _ptr(out.indptr), _ptr(out.indices), _ptr(out.wvals),
+        _ptr(out.row_weight), _ptr(out.nnz_flags), _ptr(ws), ws_bytes, _stream()),
+        'overlap_bilinear_csr')
+    _count('overlap_bilinear_csr')
+    return out
+
+
+def pool_weighted(feat_cellmajor: torch.Tensor, ov: Overlap, bw: BilinearOverlap,
+                  append_pos: bool = True) -> torch.Tensor:
+    """K2 with the bilinear weights: [n_rows, C(+2)] float32; the centroid columns and the
+    normalisation (area) come from the count matrix ``ov``."""
+    _require_cuda(feat_cellmajor)
+    n, ncell, C = feat_cellmajor.shape
+    assert n == ov.n_img and ncell == ov.fh * ov.fw and feat_cellmajor.is_contiguous()
+    D = C + (2 if append_pos else 0)
+    ld = padded_ld(D)
+    out = torch.empty((ov.n_rows, ld), dtype=torch.float32, device=feat_cellmajor.device)
+    check(_lib.load().spalign_pool_weighted(
+        _ptr(feat_cellmajor), n, C, ov.fh, ov.fw, _ptr(ov.sp_off), ov.n_rows, ov.max_rows,
+        _ptr(bw.indptr), _ptr(bw.indices), _ptr(bw.wvals), _ptr(ov.area), _ptr(ov.sum_y),
+        _ptr(ov.sum_x), int(append_pos), _ptr(out), ld, _stream()), 'pool_weighted')
+    _count('pool_weighted')
+    return out[:, :D]
 
 
 # --------------------------------------------------------------------------------------

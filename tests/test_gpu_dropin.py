@@ -204,3 +204,13 @@ def test_results_scores_and_artefacts(tmp_path):
     import json
     rec = json.loads(open(tmp_path / 'result.json').read().strip())
     assert rec['road_iou'] == info['road_iou'] and rec['n_clusters'] == 4 and rec['time_kmeans'] == 0.1
+
+
+def test_superpixel_align_dropin_bilinear_mode(batch):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    labs, feats, imgs = batch
+    bsk.clear_cache()
+    got = bsk.superpixel_align(imgs[0], feats[0], labs[0], 10, 4, False, pooling='bilinear')
+    want = so.pool_dense_bilinear(labs[0], feats[0])
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, want.astype(np.float32), rtol=1e-5, atol=1e-6)

@@ -494,3 +494,34 @@ def test_kmeans_fused_iterate_equals_three_kernel_path(ops):
     for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
         want = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64), verbose=False)
         assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
+
+
+# ------------------------------------------------------------------- f2 bilinear overlap / pooling
+@pytest.mark.parametrize('H,W,fh,fw,gy,gx,dtype', [(64, 128, 8, 16, 4, 8, np.int32), (50, 70, 7, 9, 3, 4, np.int64),
+                                                  (224, 224, 28, 28, 7, 7, np.int32), (33, 47, 5, 6, 3, 3, np.int32)])
+def test_bilinear_overlap_and_pooling_match_oracle(ops, H, W, fh, fw, gy, gx, dtype):
+    labs = [synth.voronoi_labels(H, W, gy, gx, image_index=i, dtype=dtype) for i in range(2)]
+    S = gy * gx
+    C = 12
+    feats = np.stack([synth.smooth_features(C, fh, fw, seed=30 + i, radius=1) for i in range(2)])
+    t = torch.from_numpy(np.stack(labs)).to(dev())
+    ov = ops.overlap_csr(t, fh, fw, [S, S])
+    bw = ops.overlap_bilinear_csr(t, fh, fw, ov)
+    nnz = bw.validate()
+    ip = bw.indptr.cpu().numpy(); ix = bw.indices.cpu().numpy(); wv = bw.wvals.cpu().numpy()
+    assert ip[-1] == nnz
+    cell = ops.as_cellmajor(torch.from_numpy(feats).to(dev()))
+    got = ops.pool_weighted(cell, ov, bw, append_pos=True).cpu().numpy()
+    for i, lab in enumerate(labs):
+        oip, oix, owv = so.overlap_bilinear_csr(lab, fh, fw, S)
+        a, b = ip[S * i], ip[S * (i + 1)]
+        assert np.array_equal(ip[S * i:S * (i + 1) + 1] - a, oip)
+        assert np.array_equal(ix[a:b], oix)                       # same sparsity pattern, sorted
+        np.testing.assert_allclose(wv[a:b], owv, rtol=1e-12, atol=1e-14)
+        area, sy, sx = so.superpixel_stats(lab, S)
+        np.testing.assert_allclose(bw.row_weight[S * i:S * (i + 1)].cpu().numpy(), area, rtol=1e-12)
+        want = so.pool_dense_bilinear(lab, feats[i])              # notebook formulation
+        np.testing.assert_allclose(got[S * i:S * (i + 1), :C], want.astype(np.float32), rtol=1e-5, atol=1e-6)
+        assert np.array_equal(got[S * i:S * (i + 1), C], (sy / area).astype(np.float32))
+    bw2 = ops.overlap_bilinear_csr(t, fh, fw, ov)
+    assert torch.equal(bw.wvals[:nnz], bw2.wvals[:nnz])            # bit-reproducible

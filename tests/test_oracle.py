@@ -152,3 +152,25 @@ def test_create_prior_live_reference():
     lab = synth.blob_labels(40, 60, 12, seed=1)
     np.testing.assert_allclose(so.create_prior(lab, 0.75, 0.5, 0.1, 0.1),
                                ref.create_prior(lab, 0.75, 0.5, 0.1, 0.1), rtol=1e-13)
+
+
+@pytest.mark.parametrize('H,W,fh,fw,gy,gx', [(64, 128, 8, 16, 4, 8), (50, 70, 7, 9, 3, 4), (33, 47, 5, 6, 3, 3)])
+def test_bilinear_overlap_equals_dense_resize_mean(H, W, fh, fw, gy, gx):
+    lab = synth.voronoi_labels(H, W, gy, gx, image_index=2)
+    F = synth.smooth_features(6, fh, fw, seed=5, radius=1)
+    ip, ix, wv = so.overlap_bilinear_csr(lab, fh, fw)
+    area, _, _ = so.superpixel_stats(lab)
+    rows = np.repeat(np.arange(len(area)), np.diff(ip))
+    np.testing.assert_allclose(np.bincount(rows, weights=wv), area, rtol=1e-12)   # weights sum to 1 per pixel
+    for s in range(len(area)):
+        assert np.all(np.diff(ix[ip[s]:ip[s + 1]]) > 0)
+    got = so.pool_weighted(ip, ix, wv, F.reshape(6, -1).T, area)
+    np.testing.assert_allclose(got, so.pool_dense_bilinear(lab, F), rtol=1e-11, atol=1e-12)
+
+
+def test_resize_bilinear_matches_torch_align_corners():
+    torch = pytest.importorskip('torch')
+    F = synth.smooth_features(3, 7, 9, seed=1, radius=1).astype(np.float64)
+    want = torch.nn.functional.interpolate(torch.from_numpy(F)[None], size=(50, 70), mode='bilinear',
+                                           align_corners=True)[0].numpy()
+    np.testing.assert_allclose(so.resize_bilinear(F, 50, 70), want, rtol=1e-12, atol=1e-12)
