@@ -187,13 +187,20 @@ int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, 
                          spalign_stream_t stream);
 /* sweep + reduce + update in ONE launch (single-GPU): the chunk of a group that finishes last
  * (arrival ticket in counters[G], zero on entry and on exit) sums the group's partials in
- * chunk order and applies the update, so the result is bit-identical to the three-call form. */
+ * chunk order and applies the update, so the result is bit-identical to the three-call form.
+ * mode 2 (after one mode-1 call): `totals` is kept as RUNNING sums and only rows whose
+ * assignment changed are subtracted from their old cluster and added to the new one (float64,
+ * row order within a chunk, chunks in fixed order) -- the same sums up to float64 rounding,
+ * without re-reading unchanged rows in phase 2.
+ * xflag (optional, device int32[1], zero before the mode-0 call): the mode-0 sweep sets it when
+ * X holds a denormal / inf / NaN; when it stays 0 the mode-1 sweeps convert fp32 -> fp64 on the
+ * integer pipe instead of the (slow) FP64 pipe -- same values, exact. */
 int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
                            int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
                            const int64_t* chunks, int n_chunks, const int32_t* group_chunk_off,
                            int mode, int n_iter, int32_t* assign, double* partials,
                            double* totals, double* centers, int32_t* iters, int32_t* status,
-                           int32_t* counters, spalign_stream_t stream);
+                           int32_t* counters, int32_t* xflag, spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

@@ -34,6 +34,12 @@ constexpr int KMAX = 8;
 
 // diagnostics: [0] rows screened, [1] rows sent to the exact float64 pass
 __device__ unsigned long long g_km_stats[2];
+#ifdef KM_PROFILE
+__device__ unsigned long long g_km_prof[8];
+#define KM_TICK(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof__[i] += now__ - last__; last__ = now__; } } while (0)
+#else
+#define KM_TICK(i) do {} while (0)
+#endif
 
 struct KmArgs {
   const void* X;
@@ -71,6 +77,7 @@ struct KmSmem {
   int* amb;         // [TR] tile rows that need the exact float64 pass
   int* namb;        // [1]
   int* changed;     // [1]
+  unsigned long long* bar;  // [2] mbarrier per tile buffer
 };
 
 __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
@@ -106,30 +113,87 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += sizeof(int);
   if (s) s->changed = reinterpret_cast<int*>(base + o);
   o += sizeof(int);
+  o = (o + 15) & ~(size_t)15;
+  if (s) s->bar = reinterpret_cast<unsigned long long*>(base + o);
+  o += 2 * sizeof(unsigned long long);
   return o + 64;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) with an mbarrier per tile buffer ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
 }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  // bounded spin: a byte-count mismatch must fault, never hang the GPU
+  for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 28)) __trap();
 }
 
+// warp 0 issues the tile: lane r copies row r with one bulk copy into the padded shared-memory
+// layout; lane 0 first posts the expected byte count of the whole tile
 template <typename XT>
-__device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, int64_t row0, int nvalid) {
-  const char* src = reinterpret_cast<const char*>(a.X);
+__device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, unsigned long long* bar,
+                                           int64_t row0, int nvalid) {
   const int lane = threadIdx.x & 31;
-  for (int r = threadIdx.x >> 5; r < nvalid; r += KM_THREADS / 32) {
-    const char* g = src + ((size_t)(row0 + r) * a.ldx) * sizeof(XT);
-    char* d = buf + (size_t)r * a.srow;
-    for (int c = lane; c < a.copy16; c += 32) cp_async16(d + (size_t)c * 16, g + (size_t)c * 16);
+  const char* src = reinterpret_cast<const char*>(a.X);
+  if ((size_t)a.ldx * sizeof(XT) == (size_t)a.srow) {
+    // the global row stride equals the padded shared-memory stride (e.g. 516-float descriptor
+    // rows): the whole tile is one contiguous block -> a single bulk copy
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)a.srow * (unsigned)nvalid;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(buf, src + (size_t)row0 * a.srow, bytes, bar);
+    }
+    return;
   }
+  const unsigned row_bytes = (unsigned)a.copy16 * 16u;
+  if (lane == 0) mbar_expect_tx(bar, row_bytes * (unsigned)nvalid);
+  __syncwarp();
+  for (int r = lane; r < nvalid; r += 32)
+    bulk_g2s(buf + (size_t)r * a.srow, src + ((size_t)(row0 + r) * a.ldx) * sizeof(XT), row_bytes,
+             bar);
+}
+
+// fp32 -> fp64 on the integer pipe.  B200's FP64 pipe runs at ~1/16 of the FP32 rate and phase
+// 2 is bound by it; F2F.F64.F32 runs on that pipe too.  Exact for zeros and normal numbers;
+// the init sweep (mode 0) checks every element once and the fast path is only taken when the
+// matrix holds no denormal / inf / NaN (xflag == 0).
+__device__ __forceinline__ double f2d_normal(float x) {
+  const unsigned b = __float_as_uint(x);
+  const unsigned em = b & 0x7fffffffu;
+  const unsigned hi = (b & 0x80000000u) | ((em >> 3) + (em ? 0x38000000u : 0u));
+  return __hiloint2double((int)hi, (int)(em << 29));
+}
+__device__ __forceinline__ bool f32_special(float x) {  // denormal, inf or NaN
+  const unsigned em = __float_as_uint(x) & 0x7fffffffu;
+  return em != 0u && (em - 0x00800000u) >= 0x7f000000u;
 }
 
 // virtual position columns of global row n (direct_clustering.py:300-303): (x, y) cell index
@@ -162,7 +226,8 @@ __device__ __forceinline__ int np_argmin(const double (&d)[KT], int K) {
 template <typename XT, int KT, int NS2, int R>
 __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_t row_begin,
                                          int64_t row_end, int mode, int32_t* __restrict__ assign,
-                                         double (&acc)[KT][NS2][2]) {
+                                         double (&acc)[KT][NS2][2], unsigned& tile_base,
+                                         int32_t* xflag = nullptr) {
   constexpr int VE = 16 / (int)sizeof(XT);
   constexpr bool kF32 = sizeof(XT) == 4;
   const int t = threadIdx.x;
@@ -177,34 +242,47 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   // lane k of warp 0: running sum(omega), count, sum(omega*px), sum(omega*py) of cluster k
   double e_w = 0.0, e_n = 0.0, e_x = 0.0, e_y = 0.0;
 
-  if (ntiles > 0) {
-    issue_tile<XT>(a, s.buf0, row_begin, (int)min((int64_t)TR, N));
-    cp_async_commit();
-  }
+  // tile `ti` lands in buffer ti&1 and completes phase (ti>>1)&1 of that buffer's mbarrier,
+  // counted from `tile_base` (tiles this CTA has already streamed through the barriers)
+  if (ntiles > 0 && t < 32)
+    issue_tile<XT>(a, s.buf0 + (size_t)(tile_base & 1) * s.tile_bytes, s.bar + (tile_base & 1),
+                   row_begin, (int)min((int64_t)TR, N));
+#ifdef KM_PROFILE
+  long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long last__ = clock64();
+#endif
+  // fast conversion only for fp32 rows that the init sweep found free of special values
+  const bool fastcvt = kF32 && mode != 0 && xflag != nullptr && *xflag == 0;
+  bool saw_special = false;
   const int lane_ = t & 31, wq_ = t >> 5;
   int* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
   double* my_om = s.om + wq_ * 32;
   for (int ti = 0; ti < ntiles; ++ti) {
     const int64_t trow0 = row_begin + (int64_t)ti * TR;
     const int nvalid = (int)min((int64_t)TR, row_end - trow0);
-    cp_async_wait<0>();                    // this thread's copies of tile ti have landed
+    const unsigned gt = tile_base + (unsigned)ti;   // tile counter across sweeps
     if (t == 0) *s.namb = 0;
     // every warp keeps the old assignment / prior weight of tile row `lane` (L2 hits)
+    // (mode 2 uses two lanes per row: lane r adds row r to its new cluster, lane TR + r
+    // removes it from the old one)
     int pre_a = -1;
     double pre_w = 0.0;
-    if (lane_ < nvalid) {
-      pre_a = assign[trow0 + lane_];
-      if (mode == 1) pre_w = a.w[trow0 + lane_];
+    const int prow = lane_ & (TR - 1);
+    if (lane_ < 2 * TR && lane_ < 32 && prow < nvalid) {
+      pre_a = assign[trow0 + prow];
+      if (mode != 0) pre_w = a.w[trow0 + prow];
     }
-    __syncthreads();  // (A) tile ti visible; all warps are past phase 2 of tile ti-1
-    if (ti + 1 < ntiles) {  // prefetch the next tile into the buffer phase 2 just released
-      issue_tile<XT>(a, s.buf0 + (size_t)((ti + 1) & 1) * s.tile_bytes, trow0 + TR,
-                     (int)min((int64_t)TR, row_end - (trow0 + TR)));
-      cp_async_commit();
-    }
-    const char* tile = s.buf0 + (size_t)(ti & 1) * s.tile_bytes;
+    __syncthreads();  // (A) all warps are past phase 2 of tile ti-1: its buffer is free
+    KM_TICK(0);
+    if (ti + 1 < ntiles && t < 32)  // prefetch the next tile into the buffer just released
+      issue_tile<XT>(a, s.buf0 + (size_t)((gt + 1) & 1) * s.tile_bytes, s.bar + ((gt + 1) & 1),
+                     trow0 + TR, (int)min((int64_t)TR, row_end - (trow0 + TR)));
+    KM_TICK(5);
+    mbar_wait(s.bar + (gt & 1), (gt >> 1) & 1);     // tile ti has landed
+    const char* tile = s.buf0 + (size_t)(gt & 1) * s.tile_bytes;
+    KM_TICK(1);
 
-    if (mode == 1) {
+    if (mode != 0) {
       if (kF32) {
         // ---- phase 1 (fp32 screening): one warp owns R rows, lanes stride the columns ----
         constexpr int NV = R * KT;      // partial sums per lane
@@ -418,25 +496,39 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       }
     }
 
+    KM_TICK(2);
     // ---- grouping (every warp, no block barrier): new assignment, omega, stable grouping of
     // the tile's rows by cluster into per-warp shared-memory lists ----
     int startk[KT + 1];
     {
       const int lane = lane_;
-      const bool valid = lane < nvalid;
-      int a_new = -1;
-      double om = 0.0;
+      const int half = lane >> a.logTR;          // 0: "add" entry, 1: "remove" entry (mode 2)
+      const bool in_tile = half < 2 && prow < nvalid;
+      bool valid = false;                        // this lane contributes a list entry
+      int a_new = -1;                            // cluster of the entry
+      double om = 0.0;                           // signed weight of the entry
       int chg = 0;
-      if (valid) {
-        if (mode == 1) {
-          a_new = s.anew[lane];
-          chg = a_new != pre_a;
-          om = a_new == 0 ? pre_w : 1.0 - pre_w;
-        } else {
+      if (in_tile) {
+        if (mode == 0) {
+          valid = half == 0;
           a_new = pre_a;
           om = 1.0;
+        } else {
+          const int an = s.anew[prow];
+          chg = an != pre_a;
+          if (mode == 1) {                       // full sums: every row, new cluster
+            valid = half == 0;
+            a_new = an;
+            om = an == 0 ? pre_w : 1.0 - pre_w;
+          } else if (chg) {                      // incremental: only rows that moved
+            valid = true;
+            a_new = half == 0 ? an : pre_a;
+            const double o = a_new == 0 ? pre_w : 1.0 - pre_w;
+            om = half == 0 ? o : -o;
+          }
         }
       }
+      const int an_row = (mode != 0 && in_tile) ? s.anew[prow] : pre_a;
       int pos = 0, base = 0;
       const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -450,26 +542,29 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       }
       startk[KT] = base;
       if (valid && a_new >= 0 && a_new < K) {
-        my_order[pos] = lane;
+        my_order[pos] = prow | (half << 8);      // bit 8: the entry removes the row
         my_om[pos] = om;
       }
-      const unsigned cm = __ballot_sync(0xffffffffu, chg != 0);
+      const unsigned cm = __ballot_sync(0xffffffffu, chg != 0 && half == 0);
       __syncwarp();
-      if (wq_ == 0) {  // warp 0 owns the side effects
-        if (chg) assign[trow0 + lane] = a_new;
+      if (wq_ == 0) {  // warp 0 owns the assignment write-back
+        if (chg && half == 0) assign[trow0 + prow] = an_row;
         if (lane == 0 && cm) *s.changed += __popc(cm);
-        if (lane < K) {  // lane k: per-cluster scalars, rows in order
+      }
+      if (wq_ == 1) {  // warp 1 owns the per-cluster scalars
+        if (lane < K) {  // lane k: sum(omega), count, virtual columns; rows in order
           int i0 = 0, i1 = 0;
 #pragma unroll
           for (int k = 0; k < KT; ++k)
             if (k == lane) { i0 = startk[k]; i1 = startk[k + 1]; }
           for (int i = i0; i < i1; ++i) {
             const double o = my_om[i];
+            const int ent = my_order[i];
             e_w += o;
-            e_n += 1.0;
+            e_n += (ent & 0x100) ? -1.0 : 1.0;
             if (a.pos_mode) {
               double px, py;
-              virtual_pos(a, trow0 + my_order[i], &px, &py);
+              virtual_pos(a, trow0 + (ent & 0xff), &px, &py);
               e_x = fma(o, px, e_x);
               e_y = fma(o, py, e_y);
             }
@@ -478,6 +573,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       }
     }
 
+    KM_TICK(3);
     // ---- phase 2: centroid sums, cluster by cluster, rows in order ----
 #pragma unroll
     for (int sl = 0; sl < NS2; ++sl) {
@@ -490,12 +586,19 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll 4
             for (int i = startk[k]; i < i1; ++i) {
               const double om = my_om[i];
-              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)my_order[i] * a.srow);
+              const XT* xr =
+                  reinterpret_cast<const XT*>(tile + (size_t)(my_order[i] & 0xff) * a.srow);
               double x0, x1;
               if (kF32) {
                 const float2 v = *reinterpret_cast<const float2*>(xr + c0);
-                x0 = (double)v.x;
-                x1 = (double)v.y;
+                if (fastcvt) {
+                  x0 = f2d_normal(v.x);
+                  x1 = f2d_normal(v.y);
+                } else {
+                  x0 = (double)v.x;
+                  x1 = (double)v.y;
+                  if (mode == 0) saw_special |= f32_special(v.x) | f32_special(v.y);
+                }
               } else {
                 const double2 v = *reinterpret_cast<const double2*>(xr + c0);
                 x0 = v.x;
@@ -512,20 +615,31 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
           if (k < K) {
             const int i1 = startk[k + 1];
             for (int i = startk[k]; i < i1; ++i) {
-              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)my_order[i] * a.srow);
+              const XT* xr =
+                  reinterpret_cast<const XT*>(tile + (size_t)(my_order[i] & 0xff) * a.srow);
+              if (kF32 && mode == 0) saw_special |= f32_special((float)xr[c0]);
               acc[k][sl][0] = fma(my_om[i], (double)xr[c0], acc[k][sl][0]);
             }
           }
         }
       }
     }
+    KM_TICK(4);
   }
+  if (kF32 && mode == 0 && xflag != nullptr && saw_special) atomicOr(xflag, 1);
   __syncthreads();
-  if (t < K) {
-    s.extra[t * 4 + 0] = e_w;
-    s.extra[t * 4 + 1] = e_n;
-    s.extra[t * 4 + 2] = e_x;
-    s.extra[t * 4 + 3] = e_y;
+#ifdef KM_PROFILE
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) atomicAdd(&g_km_prof[i], (unsigned long long)prof__[i]);
+    atomicAdd(&g_km_prof[6], (unsigned long long)ntiles);
+  }
+#endif
+  tile_base += (unsigned)ntiles;
+  if (wq_ == 1 && lane_ < K) {
+    s.extra[lane_ * 4 + 0] = e_w;
+    s.extra[lane_ * 4 + 1] = e_n;
+    s.extra[lane_ * 4 + 2] = e_x;
+    s.extra[lane_ * 4 + 3] = e_y;
   }
   __syncthreads();
 }
@@ -620,8 +734,14 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
   double acc[KT][NS2][2];
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
+  unsigned tile_base = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(s.bar + 0, 1);
+    mbar_init(s.bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 0, g.assign, acc);
+  km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 0, g.assign, acc, tile_base);
   finalize_centers<KT, NS2>(g.a, s, acc);
   int it = 0, status = SPALIGN_KM_ITER_CAP;
   while (it < g.n_iter) {
@@ -630,7 +750,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
     if (t == 0) *s.changed = 0;
     if (sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
     __syncthreads();
-    km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 1, g.assign, acc);
+    km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 1, g.assign, acc, tile_base);
     const int changed = *s.changed;  // km_sweep ends with __syncthreads
     if (changed == 0) {
       status = SPALIGN_KM_CONVERGED;
@@ -670,6 +790,7 @@ struct SweepArgs {
   int32_t* iters;
   int32_t* status_rw;
   int n_iter;
+  int32_t* xflag;         // [1] set by the mode-0 sweep when X holds denormal/inf/NaN; may be NULL
 };
 
 // centres / stop flags of one group from its reduced totals (shared by kmeans_update_kernel
@@ -716,7 +837,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int t = threadIdx.x;
   const int K = g.a.K, D = g.a.D, Dr = g.a.Dr;
-  if (g.mode == 1) {
+  if (g.mode != 0) {
     const double* c = g.centers + (size_t)grp * K * D;
     for (int i = t; i < K * D; i += KM_THREADS) {
       const int k = i / D, d = i - k * D;
@@ -726,9 +847,15 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   double acc[KT][NS2][2];
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
+  unsigned tile_base = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(s.bar + 0, 1);
+    mbar_init(s.bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  if (g.mode == 1 && sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
-  km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc);
+  if (g.mode != 0 && sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
+  km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
 #pragma unroll
@@ -777,10 +904,11 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
           for (int u = 0; u < 8; ++u) sum += v[u];
         }
         for (; c < c1; ++c) sum += __ldcg(g.partials + (size_t)c * pv + j);
-        tt[j] = sum;
+        // mode 2: the partials are deltas of the running sums (rows that changed cluster)
+        tt[j] = (g.mode == 2 && j != (int)pv - 1) ? tt[j] + sum : sum;
       }
       __syncthreads();
-      km_update_group(tt, D, K, g.mode, g.n_iter, g.centers_rw + (size_t)grp * K * D, g.iters,
+      km_update_group(tt, D, K, g.mode == 2 ? 1 : g.mode, g.n_iter, g.centers_rw + (size_t)grp * K * D, g.iters,
                       g.status_rw, grp);
       if (t == 0) g.counters[grp] = 0;
     }
@@ -1046,7 +1174,7 @@ extern "C" int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
   g.gco = nullptr; g.counters = nullptr; g.totals = nullptr; g.centers_rw = nullptr;
-  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0;
+  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.xflag = nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_sweep");
 }
@@ -1057,11 +1185,11 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
                                       int n_chunks, const int32_t* group_chunk_off, int mode,
                                       int n_iter, int32_t* assign, double* partials,
                                       double* totals, double* centers, int32_t* iters,
-                                      int32_t* status, int32_t* counters,
+                                      int32_t* status, int32_t* counters, int32_t* xflag,
                                       spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPALIGN_REQUIRE(chunks && group_chunk_off && assign && partials && totals && centers && iters &&
-                      status && counters && n_chunks > 0 && (mode == 0 || mode == 1),
+                      status && counters && n_chunks > 0 && mode >= 0 && mode <= 2,
                   "kmeans_iterate: bad arguments");
   Plan plan;
   const int Dr = D - (pos_mode ? 2 : 0);
@@ -1069,13 +1197,14 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
     set_error("kmeans_iterate: D=%d does not fit shared memory", D);
     return SPALIGN_E_UNSUPPORTED;
   }
+  if (mode == 2 && plan.TR > 16) mode = 1;  // two lanes per row need TR <= 16: recompute instead
   SweepArgs g;
   int rc = fill_args(&g.a, plan, X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K);
   if (rc) return rc;
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
   g.gco = group_chunk_off; g.counters = counters; g.totals = totals; g.centers_rw = centers;
-  g.iters = iters; g.status_rw = status; g.n_iter = n_iter;
+  g.iters = iters; g.status_rw = status; g.n_iter = n_iter; g.xflag = xflag;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_iterate");
 }
@@ -1116,6 +1245,18 @@ extern "C" int spalign_kmeans_init(const double* w, const int64_t* group_off, in
 // Diagnostics (synchronises the device): out[0] = rows that went through the fp32 screening
 // pass since the last reset, out[1] = rows that needed the exact float64 pass.
 extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
+#ifdef KM_PROFILE
+  {
+    unsigned long long p[8];
+    cudaMemcpyFromSymbol(p, g_km_prof, sizeof(p));
+    if (p[6]) {
+      fprintf(stderr, "[km_profile] tiles=%llu  cycles/tile (thread 0): barrierA %.0f | issue %.0f | tile wait %.0f | phase1+barrierB %.0f | grouping %.0f | phase2 %.0f\n",
+              p[6], (double)p[0] / p[6], (double)p[5] / p[6], (double)p[1] / p[6], (double)p[2] / p[6], (double)p[3] / p[6], (double)p[4] / p[6]);
+    }
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_km_prof, z, sizeof(z));
+  }
+#endif
   unsigned long long h[2] = {0, 0};
   SPALIGN_CUDA(cudaMemcpyFromSymbol(h, g_km_stats, sizeof(h)));
   if (out_host) {

@@ -399,7 +399,8 @@ class KMeansLarge:
     TARGET_CHUNKS = 4 * 148
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
-                 pos_row0=0, chunks_per_group=None, allreduce=None, fused=True):
+                 pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
+                 incremental=True):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -425,7 +426,10 @@ class KMeansLarge:
         self.iters = torch.zeros(self.G, dtype=torch.int32, device=dev)
         self.status = torch.full((self.G,), _lib.KM_RUNNING, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(self.G, dtype=torch.int32, device=dev)
+        self.xflag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fused = fused
+        self.incremental = incremental
+        self._full_done = False
         self._lib = _lib.load()
         self._init_done = False
 
@@ -475,13 +479,20 @@ class KMeansLarge:
         if self.n_chunks == 0:
             return
         if self.allreduce is None and self.fused:
-            # one launch per iteration: the last chunk of every group reduces and updates
+            # one launch per iteration: the last chunk of every group reduces and updates.
+            # After the first full iteration the centroid sums are maintained incrementally
+            # (mode 2: only rows that changed cluster are subtracted / added).
+            if mode == 1 and self.incremental:
+                if self._full_done:
+                    mode = 2
+                self._full_done = True
             check(self._lib.spalign_kmeans_iterate(
                 _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
                 self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
                 self.n_chunks, _ptr(self.gco), mode, self.n_iter, _ptr(self.assign),
                 _ptr(self.partials), _ptr(self.totals), _ptr(self.centers), _ptr(self.iters),
-                _ptr(self.status), _ptr(self.counters), _stream()), 'kmeans_iterate')
+                _ptr(self.status), _ptr(self.counters), _ptr(self.xflag), _stream()),
+                'kmeans_iterate')
             _count('kmeans_sweep')
             return
         check(self._lib.spalign_kmeans_sweep(

@@ -487,10 +487,13 @@ def test_kmeans_fused_iterate_equals_three_kernel_path(ops):
     w = rs.uniform(0, 1, len(X))
     init = np.concatenate([so.kmeans_init(4, w[a:b], rng=rs) for a, b in zip(off[:-1], off[1:])]).astype(np.int32)
     args = (torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()), torch.from_numpy(init).to(dev()), 4, off)
-    a = ops.KMeansLarge(*args, fused=True).run()
+    a = ops.KMeansLarge(*args, fused=True, incremental=False).run()
     b = ops.KMeansLarge(*args, fused=False).run(poll=3)
     assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
     assert torch.equal(a.status, b.status) and torch.equal(a.centers, b.centers)   # bit-identical
+    c = ops.KMeansLarge(*args, fused=True, incremental=True).run()                  # running sums
+    assert torch.equal(a.assign, c.assign) and torch.equal(a.iters, c.iters) and torch.equal(a.status, c.status)
+    torch.testing.assert_close(c.centers, a.centers, rtol=1e-11, atol=1e-11)
     for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
         want = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64), verbose=False)
         assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
