@@ -71,7 +71,8 @@ struct KmSmem {
   double* red;      // [8][KMAX] block reduction scratch of the exact pass
   double* om;       // [8 warps][32] omega by sorted position (per-warp copy)
   double* extra;    // [KMAX][4] sum(omega), count, sum(omega*px), sum(omega*py)
-  float* cnorm;     // [KMAX] upper bound of ||c_k||
+  float* cnorm;     // [KMAX] upper bound of ||g_k|| (fp32 screening)
+  double* hk;       // [KMAX] screening constants (hk[0]: magnitude scale)
   int* order;       // [8 warps][32] tile rows grouped by cluster (per-warp copy)
   int* anew;        // [TR] new assignment per tile row (-1: undecided)
   int* amb;         // [TR] tile rows that need the exact float64 pass
@@ -101,6 +102,8 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += (size_t)8 * 32 * sizeof(double);
   if (s) s->extra = reinterpret_cast<double*>(base + o);
   o += (size_t)KMAX * 4 * sizeof(double);
+  if (s) s->hk = reinterpret_cast<double*>(base + o);
+  o += KMAX * sizeof(double);
   if (s) s->cnorm = reinterpret_cast<float*>(base + o);
   o += KMAX * sizeof(float);
   if (s) s->order = reinterpret_cast<int*>(base + o);
@@ -295,37 +298,35 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
+        // Screening works on DIFFERENCES of squared distances to cluster 0:
+        //   delta_k = d_k^2 - d_0^2 = sum_d g_k[d]*x[d] - h_k,  g_k = 2(c_0 - c_k),
+        //   h_k = sum_d (c_0[d]^2 - c_k[d]^2),
+        // so a row costs K-1 dot products plus its squared norm (K FFMA per element instead of
+        // 2K), and the argmin over {0, delta_1, ...} is the argmin over the distances.  The first
+        // main_d = Dr & ~127 columns go through fp32; the few remaining stored columns (for the
+        // 514-column descriptors: the centroid coordinates, the large-magnitude ones) and the
+        // virtual columns are added in float64 by the lane that finishes the row.
         const int main_d = Dr & ~127;
         const char* xw = tile + (size_t)rbase * a.srow;
         for (int d = lane * 4; d < main_d; d += 128) {
           float4 xv[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
+          for (int r = 0; r < R; ++r) {
             xv[r] = *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const float4 cv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              float df = xv[r].x - cv.x; a1[r][k] = fmaf(df, df, a1[r][k]);
-              df = xv[r].y - cv.y; a1[r][k] = fmaf(df, df, a1[r][k]);
-              df = xv[r].z - cv.z; a1[r][k] = fmaf(df, df, a1[r][k]);
-              df = xv[r].w - cv.w; a1[r][k] = fmaf(df, df, a1[r][k]);
-            }
+            a1[r][0] = fmaf(xv[r].x, xv[r].x, a1[r][0]);
+            a1[r][0] = fmaf(xv[r].y, xv[r].y, a1[r][0]);
+            a1[r][0] = fmaf(xv[r].z, xv[r].z, a1[r][0]);
+            a1[r][0] = fmaf(xv[r].w, xv[r].w, a1[r][0]);
           }
-        }
-        for (int d = main_d + lane; d < Dr; d += 32) {  // columns past the last multiple of 128
-          float xs[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            xs[r] = reinterpret_cast<const float*>(xw + (size_t)r * a.srow)[d];
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const float c = s.cen32[(size_t)k * a.Dc + d];
+          for (int k = 1; k < KT; ++k) {
+            const float4 gv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              const float df = xs[r] - c;
-              a1[r][k] = fmaf(df, df, a1[r][k]);
+              a1[r][k] = fmaf(xv[r].x, gv.x, a1[r][k]);
+              a1[r][k] = fmaf(xv[r].y, gv.y, a1[r][k]);
+              a1[r][k] = fmaf(xv[r].z, gv.z, a1[r][k]);
+              a1[r][k] = fmaf(xv[r].w, gv.w, a1[r][k]);
             }
           }
         }
@@ -345,46 +346,62 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
           for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         }
-        // lane r (< R) finishes row rbase + r: fp32 argmin proved by a rounding-error bound.
-        // |F_k - D_k| <= 2u*sqrt(D_k)*||c_k|| + (2u + gamma)*D_k + (2u*||c_k||)^2, u = 2^-24
-        // (centre rounding to fp32, subtraction rounding, fp32 accumulation); the constants are
-        // generous (2^-22 and 256u).  A row is decided only when every other cluster stays
-        // strictly farther after both bounds are applied; NaN/inf never decide.
+        // lane r (< R) finishes row rbase + r.  Rounding of the fp32 part: g is rounded once
+        // (u = 2^-24) and the accumulation depth is <= 34 (16 per lane, 16 in the transpose, 2
+        // shuffles), so |dot_k - exact| <= 36u * sum|x||g_k| <= 36u * ||x|| * ||g_k||; we use
+        // eta = 2^-17 (3.5x that) with ||x||, ||g_k|| rounded up.  On top, a floor of 2^-30 times
+        // the magnitude scale keeps float64-rounding-sized gaps undecided.  A row is decided only
+        // when every other cluster stays strictly farther after both bounds; NaN/inf never decide.
         float F[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) F[k] = __shfl_sync(0xffffffffu, tot, (lane % R) * KT + k);
         if (lane < R && rbase + lane < nvalid) {
           const int rr = rbase + lane;
-          if (a.pos_mode) {
-            double dpx, dpy;
-            virtual_pos(a, trow0 + rr, &dpx, &dpy);
-            const float px = (float)dpx, py = (float)dpy;
+          double delta[KT];
+          delta[0] = 0.0;
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              const float dx = px - s.cen32[(size_t)k * a.Dc + Dr];
-              const float dy = py - s.cen32[(size_t)k * a.Dc + Dr + 1];
-              F[k] = fmaf(dx, dx, F[k]);
-              F[k] = fmaf(dy, dy, F[k]);
+          for (int k = 1; k < KT; ++k) delta[k] = (double)F[k] - s.hk[k];
+          // stored columns past main_d and the virtual columns, exactly, in float64
+          double tail2 = 0.0;
+          const float* xrow = reinterpret_cast<const float*>(tile + (size_t)rr * a.srow);
+          for (int d = main_d; d < a.D; ++d) {
+            double xv;
+            if (d < Dr) {
+              xv = (double)xrow[d];
+            } else {
+              double px, py;
+              virtual_pos(a, trow0 + rr, &px, &py);
+              xv = d == Dr ? px : py;
+            }
+            tail2 = fma(xv, xv, tail2);
+            const double c0 = s.cen[d];
+#pragma unroll
+            for (int k = 1; k < KT; ++k) {
+              if (k < K) {
+                const double ck = s.cen[(size_t)k * a.Dc + d];
+                delta[k] = fma(c0 - ck, 2.0 * xv - c0 - ck, delta[k]);
+              }
             }
           }
           int j = 0;
-          float best = F[0];
+          double best = 0.0;
 #pragma unroll
           for (int k = 1; k < KT; ++k)
-            if (F[k] < best) { best = F[k]; j = k; }
-          const float c1 = 2.4e-7f, c2 = 1.6e-5f;
-          float B[KT];
-          float lim = 0.f;
+            if (delta[k] < best) { best = delta[k]; j = k; }
+          const float nx = sqrtf(F[0]) * 1.0001f;
+          const double floor_ = 9.4e-10 * ((double)F[0] + tail2 + s.hk[0]);   // 2^-30 * scale
+          double B[KT];
+          B[0] = 0.0;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const float cn = c1 * s.cnorm[k];
-            B[k] = cn * sqrtf(F[k]) + c2 * F[k] + cn * cn;
-            if (k == j) lim = F[k] + B[k];
-          }
-          bool certain = (lim == lim) && (lim < 3.0e38f) && (j < K);
+          for (int k = 1; k < KT; ++k) B[k] = 7.63e-6 * (double)(nx * s.cnorm[k]);
+          double Bj = 0.0;
+#pragma unroll
+          for (int k = 1; k < KT; ++k)
+            if (k == j) Bj = B[k];
+          bool certain = (best == best) && (F[0] < 3.0e38f) && (j < K);
 #pragma unroll
           for (int k = 0; k < KT; ++k)
-            if (k != j) certain = certain && (F[k] - B[k] > lim);
+            if (k != j) certain = certain && (delta[k] - best > B[k] + Bj + floor_);
           s.anew[rr] = certain ? j : -1;
           if (!certain) s.amb[atomicAdd(s.namb, 1)] = rr;
         }
@@ -685,23 +702,49 @@ __device__ __forceinline__ bool finalize_centers(const KmArgs& a, const KmSmem s
 // row undecided, so the hot loops need no per-cluster guards.
 template <int KT>
 __device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) {
+  // rows 1..KT-1 of cen32 hold g_k = 2(c_0 - c_k) over the fp32 columns [0, main_d); hk[k] the
+  // matching constant sum(c_0^2 - c_k^2); cnorm[k] an upper bound of ||g_k||; hk[0] the largest
+  // ||c_k||^2 (magnitude scale of the float64 floor).  Clusters K..KT-1 of the unrolled kernel
+  // get g = 0 and a huge delta: they never win and never make a row undecided.
   const int t = threadIdx.x;
+  const int main_d = a.Dr & ~127;
   for (int i = t; i < KT * a.Dc; i += KM_THREADS) {
     const int k = i / a.Dc, d = i - k * a.Dc;
-    s.cen32[i] = k < a.K ? (d < a.D ? (float)s.cen[i] : 0.f) : (d < a.D ? 1.0e15f : 0.f);
+    float g = 0.f;
+    if (k >= 1 && k < a.K && d < main_d) g = (float)(2.0 * (s.cen[d] - s.cen[i]));
+    s.cen32[i] = g;
   }
   const int wq = t >> 5, lane = t & 31;
   if (wq < KT) {
-    double sum = 0.0;
+    double h = 0.0, g2 = 0.0, c2 = 0.0;
     if (wq < a.K) {
       for (int d = lane; d < a.D; d += 32) {
-        const double c = s.cen[(size_t)wq * a.Dc + d];
-        sum = fma(c, c, sum);
+        const double c0 = s.cen[d], ck = s.cen[(size_t)wq * a.Dc + d];
+        c2 = fma(ck, ck, c2);
+        if (d < main_d) {
+          h = fma(c0 - ck, c0 + ck, h);
+          const double g = 2.0 * (c0 - ck);
+          g2 = fma(g, g, g2);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s.cnorm[wq] = wq < a.K ? (float)sqrt(sum) * 1.000001f : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      h += __shfl_xor_sync(0xffffffffu, h, o);
+      g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (lane == 0) {
+      s.cnorm[wq] = wq < a.K ? (float)sqrt(g2) * 1.0001f : 0.f;
+      s.red[wq] = c2;                                  // ||c_k||^2, gathered below
+      if (wq >= 1) s.hk[wq] = wq < a.K ? h : -1.0e300;  // delta = dot - h: dummies are far away
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    double m = 0.0;
+    for (int k = 0; k < a.K; ++k) m = fmax(m, s.red[k]);   // NaN centres: fmax skips them,
+    s.hk[0] = m;                                            // the row test catches NaN deltas
   }
   __syncthreads();
 }
