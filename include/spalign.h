@@ -192,6 +192,11 @@ int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, 
  * assignment changed are subtracted from their old cluster and added to the new one (float64,
  * row order within a chunk, chunks in fixed order) -- the same sums up to float64 rounding,
  * without re-reading unchanged rows in phase 2.
+ * ub, lb (optional, float[N]) and cdelta (double[G,K]): Hamerly bounds.  Mode 1 stores, per row,
+ * an upper bound on the distance to its centre and a lower bound on the distance to any other
+ * centre; every update records how far each centre moved; a mode-2 sweep shifts the bounds by
+ * that drift and only gathers, screens and re-bounds the rows whose bounds no longer prove that
+ * the assignment is unchanged (fp32 rows, chunks of <= 1024 rows).  Results are identical.
  * xflag (optional, device int32[1], zero before the mode-0 call): the mode-0 sweep sets it when
  * X holds a denormal / inf / NaN; when it stays 0 the mode-1 sweeps convert fp32 -> fp64 on the
  * integer pipe instead of the (slow) FP64 pipe -- same values, exact. */
@@ -200,7 +205,8 @@ int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode
                            const int64_t* chunks, int n_chunks, const int32_t* group_chunk_off,
                            int mode, int n_iter, int32_t* assign, double* partials,
                            double* totals, double* centers, int32_t* iters, int32_t* status,
-                           int32_t* counters, int32_t* xflag, spalign_stream_t stream);
+                           int32_t* counters, int32_t* xflag, float* ub, float* lb,
+                           double* cdelta, spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

@@ -31,6 +31,7 @@ namespace {
 
 constexpr int KM_THREADS = 256;
 constexpr int KMAX = 8;
+constexpr int ACT_MAX = 1024;  // rows per chunk up to which stable rows are compacted away
 
 // diagnostics: [0] rows screened, [1] rows sent to the exact float64 pass
 __device__ unsigned long long g_km_stats[2];
@@ -57,6 +58,8 @@ struct KmArgs {
   int copy16;         // 16-byte chunks copied per row
   int TR;             // rows per tile (power of two, <= 32)
   int logTR;
+  float* ub;          // [N] Hamerly upper bound: distance to the assigned centre (may be NULL)
+  float* lb;          // [N] Hamerly lower bound: distance to the closest other centre
   int Kc;             // clusters the kernel variant is unrolled for (>= K)
   int part_bytes;     // size of the phase-1 partial-sum scratch
 };
@@ -79,6 +82,10 @@ struct KmSmem {
   int* namb;        // [1]
   int* changed;     // [1]
   unsigned long long* bar;  // [2] mbarrier per tile buffer
+  int* act;         // [ACT_MAX] chunk-relative indices of the rows that must be re-examined
+  float* dk;        // [KMAX] centre drift of the last update (rounded up)
+  float* dexcl;     // [KMAX] largest drift among the OTHER centres
+  int* nact;        // [1]
 };
 
 __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
@@ -119,6 +126,14 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o = (o + 15) & ~(size_t)15;
   if (s) s->bar = reinterpret_cast<unsigned long long*>(base + o);
   o += 2 * sizeof(unsigned long long);
+  if (s) s->act = reinterpret_cast<int*>(base + o);
+  o += ACT_MAX * sizeof(int);
+  if (s) s->dk = reinterpret_cast<float*>(base + o);
+  o += KMAX * sizeof(float);
+  if (s) s->dexcl = reinterpret_cast<float*>(base + o);
+  o += KMAX * sizeof(float);
+  if (s) s->nact = reinterpret_cast<int*>(base + o);
+  o += 4 * sizeof(int);
   return o + 64;
 }
 
@@ -163,9 +178,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // layout; lane 0 first posts the expected byte count of the whole tile
 template <typename XT>
 __device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, unsigned long long* bar,
-                                           int64_t row0, int nvalid) {
+                                           int64_t row0, int nvalid, const int* rows = nullptr) {
   const int lane = threadIdx.x & 31;
   const char* src = reinterpret_cast<const char*>(a.X);
+  if (rows != nullptr) {  // gathered tile: row r of the tile is chunk row rows[r]
+    const unsigned row_bytes = (unsigned)a.copy16 * 16u;
+    if (lane == 0) mbar_expect_tx(bar, row_bytes * (unsigned)nvalid);
+    __syncwarp();
+    for (int r = lane; r < nvalid; r += 32)
+      bulk_g2s(buf + (size_t)r * a.srow,
+               src + ((size_t)(row0 + rows[r]) * a.ldx) * sizeof(XT), row_bytes, bar);
+    return;
+  }
   if ((size_t)a.ldx * sizeof(XT) == (size_t)a.srow) {
     // the global row stride equals the padded shared-memory stride (e.g. 516-float descriptor
     // rows): the whole tile is one contiguous block -> a single bulk copy
@@ -223,6 +247,58 @@ __device__ __forceinline__ int np_argmin(const double (&d)[KT], int K) {
   return idx;
 }
 
+// Hamerly bounds pass over the rows [row_begin, row_begin + N) of a chunk (mode 2): shift every
+// row's bounds by the centre drift of the last update, keep the rows whose bounds no longer
+// prove a stable assignment, compacted in row order into s.act.  Returns their number.
+template <int KT>
+__device__ __forceinline__ int km_bounds_pass(const KmArgs& a, const KmSmem s, int64_t row_begin,
+                                              int N, const int32_t* __restrict__ assign,
+                                              const double* cdelta) {
+  const int t = threadIdx.x;
+  const int K = a.K;
+  if (t < KT) s.dk[t] = t < K ? __double2float_ru(cdelta[t]) : 0.f;
+  __syncthreads();
+  if (t < KT) {
+    float m = 0.f;
+    for (int k = 0; k < K; ++k)
+      if (k != t) m = fmaxf(m, s.dk[k]);
+    bool bad = false;  // NaN drift (NaN centres) must keep every row active
+    for (int k = 0; k < K; ++k) bad |= !(s.dk[k] == s.dk[k]);
+    s.dexcl[t] = bad ? __int_as_float(0x7f800000) : m;
+  }
+  if (t == 0) *s.nact = 0;
+  __syncthreads();
+  __shared__ int wcnt[KM_THREADS / 32];
+  for (int i0 = 0; i0 < N; i0 += KM_THREADS) {
+    const int i = i0 + t;
+    bool active = false;
+    if (i < N) {
+      const int64_t gr = row_begin + i;
+      const int ai = assign[gr];
+      const bool okc = ai >= 0 && ai < K;
+      const float u2 = __fadd_ru(a.ub[gr], okc ? s.dk[ai] : 0.f);
+      const float l2 = __fsub_rd(a.lb[gr], okc ? s.dexcl[ai] : 0.f);
+      a.ub[gr] = u2;
+      a.lb[gr] = l2;
+      active = !(okc && u2 < l2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if ((t & 31) == 0) wcnt[t >> 5] = __popc(m);
+    __syncthreads();
+    int before = *s.nact;
+    for (int q = 0; q < (t >> 5); ++q) before += wcnt[q];
+    if (active) s.act[before + __popc(m & ((1u << (t & 31)) - 1u))] = i;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int q = 0; q < KM_THREADS / 32; ++q) tot += wcnt[q];
+      *s.nact += tot;
+    }
+    __syncthreads();
+  }
+  return *s.nact;
+}
+
 // One pass over rows [row_begin, row_end).  mode 0: keep `assign`, omega = 1 (init means).
 // mode 1: reassign against s.cen, omega = w / 1-w.  acc[k][sl][j] accumulates stored column
 // 2*(sl*256+t)+j of cluster k; s.extra[k] receives sum(omega), count and the virtual columns.
@@ -230,18 +306,25 @@ template <typename XT, int KT, int NS2, int R>
 __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_t row_begin,
                                          int64_t row_end, int mode, int32_t* __restrict__ assign,
                                          double (&acc)[KT][NS2][2], unsigned& tile_base,
-                                         int32_t* xflag = nullptr) {
+                                         int32_t* xflag = nullptr, int nrows_in = -1) {
   constexpr int VE = 16 / (int)sizeof(XT);
   constexpr bool kF32 = sizeof(XT) == 4;
   const int t = threadIdx.x;
   const int K = a.K, Dr = a.Dr, TR = a.TR;
   const int NPART = KM_THREADS >> a.logTR;
   const int64_t N = row_end - row_begin;
-  const int ntiles = (int)((N + TR - 1) / TR);
   const int row = t & (TR - 1), part = t >> a.logTR;
   const int nch = (Dr + VE - 1) / VE;
   const int ch0 = (int)((long long)part * nch / NPART);
   const int ch1 = (int)((long long)(part + 1) * nch / NPART);
+  // Hamerly bounds (mode 2, fp32 rows): a row whose upper bound on the distance to its own
+  // centre stays below its lower bound on the distance to every other centre, after both are
+  // shifted by how far the centres moved, keeps its assignment -- it is neither loaded nor
+  // screened.  The remaining rows of the chunk are compacted (in row order) and gathered.
+  const bool bounds = kF32 && a.ub != nullptr && a.lb != nullptr;
+  const bool compact = nrows_in >= 0;   // the caller ran km_bounds_pass: rows listed in s.act
+  const int nrows = compact ? nrows_in : (int)N;
+  const int ntiles = (nrows + TR - 1) / TR;
   // lane k of warp 0: running sum(omega), count, sum(omega*px), sum(omega*py) of cluster k
   double e_w = 0.0, e_n = 0.0, e_x = 0.0, e_y = 0.0;
 
@@ -249,7 +332,8 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   // counted from `tile_base` (tiles this CTA has already streamed through the barriers)
   if (ntiles > 0 && t < 32)
     issue_tile<XT>(a, s.buf0 + (size_t)(tile_base & 1) * s.tile_bytes, s.bar + (tile_base & 1),
-                   row_begin, (int)min((int64_t)TR, N));
+                   row_begin, min(TR, nrows), compact ? s.act : nullptr);
+#define KM_ROW(r) (compact ? row_begin + (int64_t)s.act[tb + (r)] : row_begin + (int64_t)(tb + (r)))
 #ifdef KM_PROFILE
   long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long last__ = clock64();
@@ -261,8 +345,8 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   int* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
   double* my_om = s.om + wq_ * 32;
   for (int ti = 0; ti < ntiles; ++ti) {
-    const int64_t trow0 = row_begin + (int64_t)ti * TR;
-    const int nvalid = (int)min((int64_t)TR, row_end - trow0);
+    const int tb = ti * TR;                          // index of the tile's first row in the
+    const int nvalid = min(TR, nrows - tb);          // (possibly compacted) row list
     const unsigned gt = tile_base + (unsigned)ti;   // tile counter across sweeps
     if (t == 0) *s.namb = 0;
     // every warp keeps the old assignment / prior weight of tile row `lane` (L2 hits)
@@ -272,14 +356,15 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     double pre_w = 0.0;
     const int prow = lane_ & (TR - 1);
     if (lane_ < 2 * TR && lane_ < 32 && prow < nvalid) {
-      pre_a = assign[trow0 + prow];
-      if (mode != 0) pre_w = a.w[trow0 + prow];
+      pre_a = assign[KM_ROW(prow)];
+      if (mode != 0) pre_w = a.w[KM_ROW(prow)];
     }
     __syncthreads();  // (A) all warps are past phase 2 of tile ti-1: its buffer is free
     KM_TICK(0);
     if (ti + 1 < ntiles && t < 32)  // prefetch the next tile into the buffer just released
       issue_tile<XT>(a, s.buf0 + (size_t)((gt + 1) & 1) * s.tile_bytes, s.bar + ((gt + 1) & 1),
-                     trow0 + TR, (int)min((int64_t)TR, row_end - (trow0 + TR)));
+                     compact ? row_begin : row_begin + tb + TR, min(TR, nrows - (tb + TR)),
+                     compact ? s.act + tb + TR : nullptr);
     KM_TICK(5);
     mbar_wait(s.bar + (gt & 1), (gt >> 1) & 1);     // tile ti has landed
     const char* tile = s.buf0 + (size_t)(gt & 1) * s.tile_bytes;
@@ -298,35 +383,39 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
-        // Screening works on DIFFERENCES of squared distances to cluster 0:
-        //   delta_k = d_k^2 - d_0^2 = sum_d g_k[d]*x[d] - h_k,  g_k = 2(c_0 - c_k),
-        //   h_k = sum_d (c_0[d]^2 - c_k[d]^2),
-        // so a row costs K-1 dot products plus its squared norm (K FFMA per element instead of
-        // 2K), and the argmin over {0, delta_1, ...} is the argmin over the distances.  The first
+        // Screening works on DIFFERENCES of squared distances to cluster 0.  With df = x - c_0:
+        //   d_0^2 = sum df^2,   d_k^2 - d_0^2 = sum_d g_k[d]*df[d] + e_k,
+        //   g_k = 2(c_0 - c_k),  e_k = ||c_0 - c_k||^2,
+        // so a row costs one subtraction and K FFMA per element instead of 2K operations, and
+        // the argmin over {0, delta_1, ...} is the argmin over the distances.  The first
         // main_d = Dr & ~127 columns go through fp32; the few remaining stored columns (for the
         // 514-column descriptors: the centroid coordinates, the large-magnitude ones) and the
         // virtual columns are added in float64 by the lane that finishes the row.
         const int main_d = Dr & ~127;
         const char* xw = tile + (size_t)rbase * a.srow;
         for (int d = lane * 4; d < main_d; d += 128) {
-          float4 xv[R];
+          const float4 c0v = *reinterpret_cast<const float4*>(s.cen32 + d);
+          float4 df[R];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            xv[r] = *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
-            a1[r][0] = fmaf(xv[r].x, xv[r].x, a1[r][0]);
-            a1[r][0] = fmaf(xv[r].y, xv[r].y, a1[r][0]);
-            a1[r][0] = fmaf(xv[r].z, xv[r].z, a1[r][0]);
-            a1[r][0] = fmaf(xv[r].w, xv[r].w, a1[r][0]);
+            const float4 xv =
+                *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
+            df[r].x = xv.x - c0v.x; df[r].y = xv.y - c0v.y;
+            df[r].z = xv.z - c0v.z; df[r].w = xv.w - c0v.w;
+            a1[r][0] = fmaf(df[r].x, df[r].x, a1[r][0]);
+            a1[r][0] = fmaf(df[r].y, df[r].y, a1[r][0]);
+            a1[r][0] = fmaf(df[r].z, df[r].z, a1[r][0]);
+            a1[r][0] = fmaf(df[r].w, df[r].w, a1[r][0]);
           }
 #pragma unroll
           for (int k = 1; k < KT; ++k) {
             const float4 gv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              a1[r][k] = fmaf(xv[r].x, gv.x, a1[r][k]);
-              a1[r][k] = fmaf(xv[r].y, gv.y, a1[r][k]);
-              a1[r][k] = fmaf(xv[r].z, gv.z, a1[r][k]);
-              a1[r][k] = fmaf(xv[r].w, gv.w, a1[r][k]);
+              a1[r][k] = fmaf(df[r].x, gv.x, a1[r][k]);
+              a1[r][k] = fmaf(df[r].y, gv.y, a1[r][k]);
+              a1[r][k] = fmaf(df[r].z, gv.z, a1[r][k]);
+              a1[r][k] = fmaf(df[r].w, gv.w, a1[r][k]);
             }
           }
         }
@@ -346,12 +435,15 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
           for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         }
-        // lane r (< R) finishes row rbase + r.  Rounding of the fp32 part: g is rounded once
-        // (u = 2^-24) and the accumulation depth is <= 34 (16 per lane, 16 in the transpose, 2
-        // shuffles), so |dot_k - exact| <= 36u * sum|x||g_k| <= 36u * ||x|| * ||g_k||; we use
-        // eta = 2^-17 (3.5x that) with ||x||, ||g_k|| rounded up.  On top, a floor of 2^-30 times
-        // the magnitude scale keeps float64-rounding-sized gaps undecided.  A row is decided only
-        // when every other cluster stays strictly farther after both bounds; NaN/inf never decide.
+        // lane r (< R) finishes row rbase + r.  Rounding of the fp32 part (u = 2^-24): c_0 and
+        // g are rounded once, df once, and the accumulation depth is <= 34 (16 per lane, 16 in
+        // the transpose, 2 shuffles), so with d0 = ||df|| over the fp32 columns
+        //   |dot_k - exact| <= (37u*d0 + u*||c_0||) * ||g_k||,
+        //   |F_0  - exact| <= 36u*d0^2 + 2u*d0*||c_0|| + (u*||c_0||)^2.
+        // We use eta = 2^-17 (3.5x) for all of them, norms rounded up, plus a floor of 2^-30 of
+        // the magnitude scale so that float64-rounding-sized gaps stay undecided.  A row is
+        // decided only when every other cluster stays strictly farther after both bounds;
+        // NaN/inf never decide.  Decided rows also refresh their Hamerly bounds.
         float F[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) F[k] = __shfl_sync(0xffffffffu, tot, (lane % R) * KT + k);
@@ -362,7 +454,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
           for (int k = 1; k < KT; ++k) delta[k] = (double)F[k] - s.hk[k];
           // stored columns past main_d and the virtual columns, exactly, in float64
-          double tail2 = 0.0;
+          double tail0 = 0.0;   // their share of d_0^2
           const float* xrow = reinterpret_cast<const float*>(tile + (size_t)rr * a.srow);
           for (int d = main_d; d < a.D; ++d) {
             double xv;
@@ -370,11 +462,11 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
               xv = (double)xrow[d];
             } else {
               double px, py;
-              virtual_pos(a, trow0 + rr, &px, &py);
+              virtual_pos(a, KM_ROW(rr), &px, &py);
               xv = d == Dr ? px : py;
             }
-            tail2 = fma(xv, xv, tail2);
             const double c0 = s.cen[d];
+            tail0 = fma(xv - c0, xv - c0, tail0);
 #pragma unroll
             for (int k = 1; k < KT; ++k) {
               if (k < K) {
@@ -388,22 +480,37 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 #pragma unroll
           for (int k = 1; k < KT; ++k)
             if (delta[k] < best) { best = delta[k]; j = k; }
-          const float nx = sqrtf(F[0]) * 1.0001f;
-          const double floor_ = 9.4e-10 * ((double)F[0] + tail2 + s.hk[0]);   // 2^-30 * scale
+          const float d0 = sqrtf(F[0]) * 1.0001f;
+          const float c0n = s.cnorm[0];
+          const double D0 = (double)F[0] + tail0;                       // d_0^2, all columns
+          const double E0 = 7.63e-6 * ((double)F[0] + 2.0 * (double)(d0 * c0n)) +
+                            (double)(c0n * 6.0e-8f) * (double)(c0n * 6.0e-8f);
+          const double floor_ = 9.4e-10 * (D0 + s.hk[0]);               // 2^-30 * scale
           double B[KT];
           B[0] = 0.0;
 #pragma unroll
-          for (int k = 1; k < KT; ++k) B[k] = 7.63e-6 * (double)(nx * s.cnorm[k]);
+          for (int k = 1; k < KT; ++k) B[k] = 7.63e-6 * (double)((d0 + c0n) * s.cnorm[k]);
           double Bj = 0.0;
 #pragma unroll
           for (int k = 1; k < KT; ++k)
             if (k == j) Bj = B[k];
           bool certain = (best == best) && (F[0] < 3.0e38f) && (j < K);
+          double second = 1.0e300;   // smallest provable squared distance to another centre
 #pragma unroll
-          for (int k = 0; k < KT; ++k)
-            if (k != j) certain = certain && (delta[k] - best > B[k] + Bj + floor_);
+          for (int k = 0; k < KT; ++k) {
+            if (k != j) {
+              certain = certain && (delta[k] - best > B[k] + Bj + floor_);
+              second = fmin(second, D0 + delta[k] - E0 - B[k]);
+            }
+          }
           s.anew[rr] = certain ? j : -1;
-          if (!certain) s.amb[atomicAdd(s.namb, 1)] = rr;
+          if (!certain) {
+            s.amb[atomicAdd(s.namb, 1)] = rr;
+          } else if (bounds) {
+            const int64_t gr = KM_ROW(rr);
+            a.ub[gr] = __fmul_ru(__double2float_ru(sqrt(fmax(D0 + best + E0 + Bj, 0.0))), 1.000001f);
+            a.lb[gr] = __fmul_rd(__double2float_rd(sqrt(fmax(second, 0.0))), 0.999999f);
+          }
         }
         __syncthreads();
 
@@ -442,7 +549,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
           if (t == 0) {
             double dd[KT];
             double px = 0.0, py = 0.0;
-            if (a.pos_mode) virtual_pos(a, trow0 + r, &px, &py);
+            if (a.pos_mode) virtual_pos(a, KM_ROW(r), &px, &py);
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
               double sum = 0.0;
@@ -457,7 +564,19 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
               }
               dd[k] = sqrt(sum);
             }
-            s.anew[r] = np_argmin<KT>(dd, K);
+            const int jj = np_argmin<KT>(dd, K);
+            s.anew[r] = jj;
+            if (bounds) {  // exact distances: bounds with a 1e-6 relative cushion
+              double sec = 1.0e300;
+#pragma unroll
+              for (int k = 0; k < KT; ++k)
+                if (k < K && k != jj) sec = fmin(sec, dd[k]);
+              const int64_t gr = KM_ROW(r);
+              const bool okd = dd[jj] == dd[jj] && sec == sec;
+              a.ub[gr] = okd ? __fmul_ru(__double2float_ru(dd[jj]), 1.000001f)
+                             : __int_as_float(0x7f800000);
+              a.lb[gr] = okd ? __fmul_rd(__double2float_rd(sec), 0.999999f) : 0.f;
+            }
           }
           __syncthreads();
         }
@@ -492,7 +611,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
         if (t < 32 && t < nvalid && t < TR) {
           double dd[KT];
           double px = 0.0, py = 0.0;
-          if (a.pos_mode) virtual_pos(a, trow0 + t, &px, &py);
+          if (a.pos_mode) virtual_pos(a, KM_ROW(t), &px, &py);
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
             double sum = 0.0;
@@ -565,7 +684,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       const unsigned cm = __ballot_sync(0xffffffffu, chg != 0 && half == 0);
       __syncwarp();
       if (wq_ == 0) {  // warp 0 owns the assignment write-back
-        if (chg && half == 0) assign[trow0 + prow] = an_row;
+        if (chg && half == 0) assign[KM_ROW(prow)] = an_row;
         if (lane == 0 && cm) *s.changed += __popc(cm);
       }
       if (wq_ == 1) {  // warp 1 owns the per-cluster scalars
@@ -581,7 +700,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             e_n += (ent & 0x100) ? -1.0 : 1.0;
             if (a.pos_mode) {
               double px, py;
-              virtual_pos(a, trow0 + (ent & 0xff), &px, &py);
+              virtual_pos(a, KM_ROW(ent & 0xff), &px, &py);
               e_x = fma(o, px, e_x);
               e_y = fma(o, py, e_y);
             }
@@ -651,6 +770,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     atomicAdd(&g_km_prof[6], (unsigned long long)ntiles);
   }
 #endif
+#undef KM_ROW
   tile_base += (unsigned)ntiles;
   if (wq_ == 1 && lane_ < K) {
     s.extra[lane_ * 4 + 0] = e_w;
@@ -702,42 +822,48 @@ __device__ __forceinline__ bool finalize_centers(const KmArgs& a, const KmSmem s
 // row undecided, so the hot loops need no per-cluster guards.
 template <int KT>
 __device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) {
-  // rows 1..KT-1 of cen32 hold g_k = 2(c_0 - c_k) over the fp32 columns [0, main_d); hk[k] the
-  // matching constant sum(c_0^2 - c_k^2); cnorm[k] an upper bound of ||g_k||; hk[0] the largest
-  // ||c_k||^2 (magnitude scale of the float64 floor).  Clusters K..KT-1 of the unrolled kernel
-  // get g = 0 and a huge delta: they never win and never make a row undecided.
+  // cen32 row 0 = c_0 rounded to fp32, rows 1..KT-1 = g_k = 2(c_0 - c_k), all over the fp32
+  // columns [0, main_d); hk[k] = -e_k = -||c_0 - c_k||^2 over those columns (delta = dot - hk);
+  // cnorm[0] >= ||c_0||, cnorm[k] >= ||g_k||; hk[0] = largest ||c_k||^2 (magnitude scale of the
+  // float64 floor).  Clusters K..KT-1 of the unrolled kernel get g = 0 and a huge delta: they
+  // never win and never make a row undecided.
   const int t = threadIdx.x;
   const int main_d = a.Dr & ~127;
   for (int i = t; i < KT * a.Dc; i += KM_THREADS) {
     const int k = i / a.Dc, d = i - k * a.Dc;
     float g = 0.f;
-    if (k >= 1 && k < a.K && d < main_d) g = (float)(2.0 * (s.cen[d] - s.cen[i]));
+    if (d < main_d) {
+      if (k == 0) g = (float)s.cen[d];
+      else if (k < a.K) g = (float)(2.0 * (s.cen[d] - s.cen[i]));
+    }
     s.cen32[i] = g;
   }
   const int wq = t >> 5, lane = t & 31;
   if (wq < KT) {
-    double h = 0.0, g2 = 0.0, c2 = 0.0;
+    double e = 0.0, g2 = 0.0, c2 = 0.0, c2m = 0.0;
     if (wq < a.K) {
       for (int d = lane; d < a.D; d += 32) {
         const double c0 = s.cen[d], ck = s.cen[(size_t)wq * a.Dc + d];
         c2 = fma(ck, ck, c2);
         if (d < main_d) {
-          h = fma(c0 - ck, c0 + ck, h);
-          const double g = 2.0 * (c0 - ck);
-          g2 = fma(g, g, g2);
+          c2m = fma(ck, ck, c2m);
+          e = fma(c0 - ck, c0 - ck, e);
         }
       }
+      g2 = 4.0 * e;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      h += __shfl_xor_sync(0xffffffffu, h, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
       g2 += __shfl_xor_sync(0xffffffffu, g2, o);
       c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+      c2m += __shfl_xor_sync(0xffffffffu, c2m, o);
     }
     if (lane == 0) {
-      s.cnorm[wq] = wq < a.K ? (float)sqrt(g2) * 1.0001f : 0.f;
-      s.red[wq] = c2;                                  // ||c_k||^2, gathered below
-      if (wq >= 1) s.hk[wq] = wq < a.K ? h : -1.0e300;  // delta = dot - h: dummies are far away
+      if (wq == 0) s.cnorm[0] = (float)sqrt(c2m) * 1.0001f;
+      else s.cnorm[wq] = wq < a.K ? (float)sqrt(g2) * 1.0001f : 0.f;
+      s.red[wq] = c2;                                   // ||c_k||^2, gathered below
+      if (wq >= 1) s.hk[wq] = wq < a.K ? -e : -1.0e300;  // delta = dot - hk: dummies far away
     }
   }
   __syncthreads();
@@ -834,13 +960,15 @@ struct SweepArgs {
   int32_t* status_rw;
   int n_iter;
   int32_t* xflag;         // [1] set by the mode-0 sweep when X holds denormal/inf/NaN; may be NULL
+  double* cdelta;         // [G][K] centre drift of the last update (Hamerly bounds); may be NULL
 };
 
 // centres / stop flags of one group from its reduced totals (shared by kmeans_update_kernel
 // and the fused finish of kmeans_sweep_kernel); whole block, uniform control flow
 __device__ __forceinline__ void km_update_group(const double* tt, int D, int K, int mode,
                                                 int n_iter, double* c, int32_t* iters,
-                                                int32_t* status, int grp) {
+                                                int32_t* status, int grp,
+                                                double* cdelta = nullptr) {
   const int pv = K * (D + 2) + 1;
   const int t = threadIdx.x;
   __shared__ int s_stop;
@@ -853,9 +981,25 @@ __device__ __forceinline__ void km_update_group(const double* tt, int D, int K, 
     }
     return;
   }
-  for (int i = t; i < K * D; i += blockDim.x) {
-    const int k = i / D, d = i - k * D;
-    c[i] = tt[(size_t)k * (D + 2) + d] / tt[(size_t)k * (D + 2) + D];
+  // new centres; cdelta[k] = ||c_k(new) - c_k(old)|| for the Hamerly bounds (fixed-order sums)
+  __shared__ double s_d2[KMAX][8];
+  for (int k = 0; k < K; ++k) {
+    double d2 = 0.0;
+    for (int d = t; d < D; d += blockDim.x) {
+      const double nv = tt[(size_t)k * (D + 2) + d] / tt[(size_t)k * (D + 2) + D];
+      const double df = nv - c[(size_t)k * D + d];
+      d2 = fma(df, df, d2);
+      c[(size_t)k * D + d] = nv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if ((t & 31) == 0) s_d2[k][t >> 5] = d2;
+  }
+  __syncthreads();
+  if (cdelta != nullptr && t < K) {
+    double d2 = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) d2 += s_d2[t][q];
+    cdelta[(size_t)grp * K + t] = sqrt(d2) * (1.0 + 1e-12);
   }
   if (t == 0 && mode == 1) {
     const int it = iters[grp] + 1;
@@ -880,13 +1024,6 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int t = threadIdx.x;
   const int K = g.a.K, D = g.a.D, Dr = g.a.Dr;
-  if (g.mode != 0) {
-    const double* c = g.centers + (size_t)grp * K * D;
-    for (int i = t; i < K * D; i += KM_THREADS) {
-      const int k = i / D, d = i - k * D;
-      s.cen[(size_t)k * g.a.Dc + d] = c[i];
-    }
-  }
   double acc[KT][NS2][2];
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
@@ -897,8 +1034,28 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (g.mode != 0 && sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
-  km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
+  // mode 2 with Hamerly bounds: find the rows that must be re-examined before anything else;
+  // a chunk without such rows only reports zeros
+  int nrows_in = -1;
+  if (sizeof(XT) == 4 && g.mode == 2 && g.a.ub != nullptr && g.cdelta != nullptr &&
+      re - rb <= ACT_MAX)
+    nrows_in = km_bounds_pass<KT>(g.a, s, rb, (int)(re - rb), g.assign,
+                                  g.cdelta + (size_t)grp * K);
+  if (nrows_in != 0) {
+    if (g.mode != 0) {
+      const double* c = g.centers + (size_t)grp * K * D;
+      for (int i = t; i < K * D; i += KM_THREADS) {
+        const int k = i / D, d = i - k * D;
+        s.cen[(size_t)k * g.a.Dc + d] = c[i];
+      }
+      __syncthreads();
+      if (sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
+    }
+    km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag, nrows_in);
+  } else if (t < K) {
+    s.extra[t * 4 + 0] = s.extra[t * 4 + 1] = s.extra[t * 4 + 2] = s.extra[t * 4 + 3] = 0.0;
+  }
+  __syncthreads();
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* out = g.partials + (size_t)ck * pv;
 #pragma unroll
@@ -951,8 +1108,8 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
         tt[j] = (g.mode == 2 && j != (int)pv - 1) ? tt[j] + sum : sum;
       }
       __syncthreads();
-      km_update_group(tt, D, K, g.mode == 2 ? 1 : g.mode, g.n_iter, g.centers_rw + (size_t)grp * K * D, g.iters,
-                      g.status_rw, grp);
+      km_update_group(tt, D, K, g.mode == 2 ? 1 : g.mode, g.n_iter,
+                      g.centers_rw + (size_t)grp * K * D, g.iters, g.status_rw, grp, g.cdelta);
       if (t == 0) g.counters[grp] = 0;
     }
   }
@@ -1134,6 +1291,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->pos_period = pos_period ? pos_period : 1; a->pos_row0 = pos_row0; a->w = w;
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
+  a->ub = nullptr; a->lb = nullptr;
   return SPALIGN_OK;
 }
 
@@ -1217,7 +1375,7 @@ extern "C" int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
   g.gco = nullptr; g.counters = nullptr; g.totals = nullptr; g.centers_rw = nullptr;
-  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.xflag = nullptr;
+  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.xflag = nullptr; g.cdelta = nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_sweep");
 }
@@ -1229,6 +1387,7 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
                                       int n_iter, int32_t* assign, double* partials,
                                       double* totals, double* centers, int32_t* iters,
                                       int32_t* status, int32_t* counters, int32_t* xflag,
+                                      float* ub, float* lb, double* cdelta,
                                       spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPALIGN_REQUIRE(chunks && group_chunk_off && assign && partials && totals && centers && iters &&
@@ -1248,6 +1407,8 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
   g.partials = partials;
   g.gco = group_chunk_off; g.counters = counters; g.totals = totals; g.centers_rw = centers;
   g.iters = iters; g.status_rw = status; g.n_iter = n_iter; g.xflag = xflag;
+  g.cdelta = (ub && lb) ? cdelta : nullptr;
+  g.a.ub = cdelta ? ub : nullptr; g.a.lb = cdelta ? lb : nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_iterate");
 }

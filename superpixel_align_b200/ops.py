@@ -400,7 +400,7 @@ class KMeansLarge:
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
-                 incremental=True):
+                 incremental=True, bounds=True):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -427,6 +427,11 @@ class KMeansLarge:
         self.status = torch.full((self.G,), _lib.KM_RUNNING, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(self.G, dtype=torch.int32, device=dev)
         self.xflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ub = self.lb = self.cdelta = None
+        if bounds and incremental and fused and self.code == _lib.F32:
+            self.ub = torch.empty(self.N, dtype=torch.float32, device=dev)
+            self.lb = torch.empty(self.N, dtype=torch.float32, device=dev)
+            self.cdelta = torch.zeros((self.G, K), dtype=torch.float64, device=dev)
         self.fused = fused
         self.incremental = incremental
         self._full_done = False
@@ -491,8 +496,8 @@ class KMeansLarge:
                 self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
                 self.n_chunks, _ptr(self.gco), mode, self.n_iter, _ptr(self.assign),
                 _ptr(self.partials), _ptr(self.totals), _ptr(self.centers), _ptr(self.iters),
-                _ptr(self.status), _ptr(self.counters), _ptr(self.xflag), _stream()),
-                'kmeans_iterate')
+                _ptr(self.status), _ptr(self.counters), _ptr(self.xflag), _ptr(self.ub),
+                _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_iterate')
             _count('kmeans_sweep')
             return
         check(self._lib.spalign_kmeans_sweep(
@@ -521,22 +526,50 @@ class KMeansLarge:
             self.init_centers()
         self._sweep(1)
 
-    def run(self, poll: int = 4, first_poll: int = 6) -> KMeansResult:
-        """Synchronises at the poll points (after ``first_poll`` iterations, then every
-        ``poll``) to read the stop flags and drop finished groups from the chunk list."""
+    def run(self, poll: int = 4, first_poll: int = 6, blocking: bool = False,
+            lookahead: int = 2) -> KMeansResult:
+        """Iterate until every group has stopped.  The stop flags are read back asynchronously
+        (pinned buffer + event) after ``first_poll`` iterations and then every ``poll``; sweeps
+        keep being enqueued meanwhile (at most ``lookahead`` of them; CTAs of finished groups
+        exit at once), so the GPU does not idle during the round trip.  When a read-back lands, finished groups are dropped from the chunk
+        list.  ``blocking=True`` synchronises at every poll instead (deterministic launch
+        count, used by tests)."""
         if not self._init_done:
             self.init_centers()
-        done, nxt = 0, min(first_poll, self.n_iter) if self.n_iter else 0
+        done = 0
+        nxt = min(first_poll, self.n_iter)
+        pending = None
+        ahead_until = 0
+        can_recut = self.allreduce is None and self.chunks_per_group is None
+        if not blocking and getattr(self, '_pin', None) is None:
+            self._pin = torch.empty(self.G, dtype=torch.int32).pin_memory()
         while done < self.n_iter:
-            while done < nxt:
-                self._sweep(1)
-                done += 1
-            running = (self.status == _lib.KM_RUNNING).cpu().numpy()   # sync
-            if not running.any():
-                break
-            if self.allreduce is None and self.chunks_per_group is None:
-                self._set_chunks(np.nonzero(running)[0])
-            nxt = min(done + poll, self.n_iter)
+            self._sweep(1)
+            done += 1
+            if blocking:
+                if done >= nxt:
+                    running = (self.status == _lib.KM_RUNNING).cpu().numpy()   # sync
+                    if not running.any():
+                        break
+                    if can_recut:
+                        self._set_chunks(np.nonzero(running)[0])
+                    nxt = min(done + poll, self.n_iter)
+                continue
+            if pending is None and done >= nxt:
+                self._pin.copy_(self.status, non_blocking=True)
+                pending = torch.cuda.Event()
+                pending.record()
+                ahead_until = done + lookahead
+            if pending is not None and (pending.query() or done >= ahead_until
+                                        or done >= self.n_iter):
+                pending.synchronize()
+                running = self._pin.numpy() == _lib.KM_RUNNING
+                pending = None
+                if not running.any():
+                    break
+                if can_recut:
+                    self._set_chunks(np.nonzero(running)[0])
+                nxt = done + poll
         if self.n_iter == 0:
             self.status.fill_(_lib.KM_ITER_CAP)
         return KMeansResult(self.assign, self.iters, self.status, self.centers)
