@@ -207,6 +207,20 @@ int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode
                            double* totals, double* centers, int32_t* iters, int32_t* status,
                            int32_t* counters, int32_t* xflag, float* ub, float* lb,
                            double* cdelta, spalign_stream_t stream);
+/* Runs every group that is still SPALIGN_KM_RUNNING to its stop condition in ONE launch: one
+ * persistent CTA per group repeats mode-2 iterations (bounds pass, gather + screen the rows the
+ * bounds cannot prove stable, move the changed rows between the running sums, new centres,
+ * drift) without leaving the SM.  Preconditions: fp32 rows; spalign_kmeans_iterate has run
+ * mode 0 and at least one mode-1 iteration with ub/lb/cdelta, so totals/centers/cdelta/ub/lb
+ * are current.  group_off: device int64[G+1] row ranges.  Same stop rules and results as
+ * repeating spalign_kmeans_iterate (batch_spalign_kmeans.py:152-179); meant for many groups
+ * of at most a few thousand rows each (per-image clustering), where it replaces one launch
+ * and one host poll per iteration. */
+int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                          int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
+                          const int64_t* group_off, int G, int n_iter, int32_t* assign,
+                          double* totals, double* centers, int32_t* iters, int32_t* status,
+                          float* ub, float* lb, double* cdelta, spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

@@ -1115,6 +1115,153 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   }
 }
 
+struct TailArgs {
+  KmArgs a;
+  const int64_t* group_off;  // [G+1]
+  int32_t* assign;
+  double* totals;            // [G][K*(D+2)+1] running sums left by the full iteration
+  double* centers;           // [G][K][D]
+  int32_t* iters;
+  int32_t* status;
+  double* cdelta;            // [G][K]
+  int n_iter;
+};
+
+// Remaining iterations of one group by one persistent CTA (fp32 rows, after the first full
+// iteration of kmeans_sweep_kernel has left running sums, centres, centre drift and Hamerly
+// bounds).  Every iteration is a mode-2 sweep: bounds pass, gather + screen only the rows the
+// bounds cannot prove stable, move the rows that changed cluster between the running sums,
+// new centres and drift -- all without leaving the SM, so an iteration costs a few
+// microseconds instead of a launch, and groups proceed independently of each other.
+template <typename XT, int KT, int NS2, int R, int MINB>
+__global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs g) {
+  extern __shared__ __align__(128) char smem_raw[];
+  if (sizeof(XT) != 4) return;  // host side refuses float64 rows
+  KmSmem s;
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
+  const int grp = blockIdx.x;
+  if (g.status[grp] != SPALIGN_KM_RUNNING) return;
+  const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
+  const int t = threadIdx.x;
+  const int K = g.a.K, D = g.a.D, Dr = g.a.Dr, Dc = g.a.Dc;
+  const size_t pv = (size_t)K * (D + 2) + 1;
+  double* tt = g.totals + (size_t)grp * pv;
+  double* cg = g.centers + (size_t)grp * K * D;
+  double* cd = g.cdelta + (size_t)grp * K;
+  __shared__ double xs[KMAX * 4];
+  if (t == 0) {
+    mbar_init(s.bar + 0, 1);
+    mbar_init(s.bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = t; i < K * D; i += KM_THREADS) {
+    const int k = i / D, d = i - k * D;
+    s.cen[(size_t)k * Dc + d] = cg[i];
+  }
+  __syncthreads();
+  int it = g.iters[grp];
+  int status = SPALIGN_KM_ITER_CAP;
+  unsigned tile_base = 0;
+  double acc[KT][NS2][2];
+  while (it < g.n_iter) {
+    zero_acc<KT, NS2>(acc);
+    if (t == 0) *s.changed = 0;
+    if (t < KMAX * 4) xs[t] = 0.0;
+    prepare_screen<KT>(g.a, s);  // ends with a block barrier
+    for (int64_t rb = r0; rb < r1; rb += ACT_MAX) {
+      const int n = (int)min((int64_t)ACT_MAX, r1 - rb);
+      const int na = km_bounds_pass<KT>(g.a, s, rb, n, g.assign, cd);
+      if (na > 0) {
+        km_sweep<XT, KT, NS2, R>(g.a, s, rb, rb + n, 2, g.assign, acc, tile_base, nullptr, na);
+        if (t < K * 4) xs[t] += s.extra[t];
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    ++it;
+    if (*s.changed == 0) {  // assignment unchanged: centres stay
+      status = SPALIGN_KM_CONVERGED;
+      break;
+    }
+    // running sums += this iteration's moves; new centres and their drift
+    if (t < K) {
+      double* e = tt + (size_t)t * (D + 2);
+      const double ws = e[D] + xs[t * 4 + 0];
+      const double cnt = e[D + 1] + xs[t * 4 + 1];
+      e[D] = ws;
+      e[D + 1] = cnt;
+      double dp = 0.0;
+      if (g.a.pos_mode) {
+        const double sx = e[Dr] + xs[t * 4 + 2], sy = e[Dr + 1] + xs[t * 4 + 3];
+        e[Dr] = sx;
+        e[Dr + 1] = sy;
+        const double nx = sx / ws, ny = sy / ws;
+        const double dx = nx - s.cen[(size_t)t * Dc + Dr], dy = ny - s.cen[(size_t)t * Dc + Dr + 1];
+        dp = fma(dx, dx, dy * dy);
+        s.cen[(size_t)t * Dc + Dr] = nx;
+        s.cen[(size_t)t * Dc + Dr + 1] = ny;
+      }
+      s.extra[t * 4 + 0] = ws;
+      s.extra[t * 4 + 1] = cnt;
+      s.extra[t * 4 + 2] = dp;
+    }
+    __syncthreads();
+    double d2[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) d2[k] = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < NS2; ++sl) {
+      const int c0 = 2 * (sl * KM_THREADS + t);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        if (k < K) {
+          const double ws = s.extra[k * 4 + 0];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (c0 + j < Dr) {
+              const size_t idx = (size_t)k * (D + 2) + c0 + j;
+              const double v = tt[idx] + acc[k][sl][j];
+              tt[idx] = v;
+              const double nv = v / ws;
+              const double df = nv - s.cen[(size_t)k * Dc + c0 + j];
+              d2[k] = fma(df, df, d2[k]);
+              s.cen[(size_t)k * Dc + c0 + j] = nv;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], o);
+      if ((t & 31) == 0) s.red[(size_t)(t >> 5) * KMAX + k] = d2[k];
+    }
+    __syncthreads();
+    if (t < K) {
+      double sum = s.extra[t * 4 + 2];
+      for (int q = 0; q < KM_THREADS / 32; ++q) sum += s.red[(size_t)q * KMAX + t];
+      cd[t] = sqrt(sum) * (1.0 + 1e-12);
+    }
+    bool empty = false;
+    for (int k = 0; k < K; ++k) empty |= (s.extra[k * 4 + 1] == 0.0);
+    if (empty) {
+      status = SPALIGN_KM_EMPTY_CLUSTER;
+      break;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = t; i < K * D; i += KM_THREADS) {
+    const int k = i / D, d = i - k * D;
+    cg[i] = s.cen[(size_t)k * Dc + d];
+  }
+  if (t == 0) {
+    g.iters[grp] = it;
+    g.status[grp] = status;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 kmeans_reduce_kernel(const double* __restrict__ partials, const int32_t* __restrict__ gco,
                      int pv, double* __restrict__ totals) {
@@ -1227,7 +1374,7 @@ struct Plan {
   size_t smem;
 };
 
-bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
+bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p, int max_tr = 32) {
   const int es = x_dtype == SPALIGN_F32 ? 4 : 8;
   const int row_bytes = (int)align_up((size_t)Dr * es, 16);
   int srow = row_bytes;
@@ -1263,6 +1410,7 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p) {
     int r = cands[i];
     if (!small && r == 4) continue;
     if (small && r == 1) continue;
+    if (8 * r > max_tr) continue;
     const int pb = (KM_THREADS / 32) * (r * p->Kc) * 33 * (int)sizeof(float);
     size_t bytes = km_carve(nullptr, nullptr, 8 * r, srow, K, p->Dc, p->Kc, pb);
     if (bytes <= limit) {
@@ -1411,6 +1559,33 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
   g.a.ub = cdelta ? ub : nullptr; g.a.lb = cdelta ? lb : nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_iterate");
+}
+
+extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode,
+                                     int pos_w, int64_t pos_period, int64_t pos_row0,
+                                     const double* w, int D, int K, const int64_t* group_off,
+                                     int G, int n_iter, int32_t* assign, double* totals,
+                                     double* centers, int32_t* iters, int32_t* status, float* ub,
+                                     float* lb, double* cdelta, spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(group_off && assign && totals && centers && iters && status && ub && lb &&
+                      cdelta && G > 0 && n_iter >= 0,
+                  "kmeans_finish: bad arguments");
+  SPALIGN_REQUIRE(x_dtype == SPALIGN_F32, "kmeans_finish: fp32 rows only");
+  Plan plan;
+  const int Dr = D - (pos_mode ? 2 : 0);
+  if (!make_plan(x_dtype, D, Dr, K, &plan, 16)) {
+    set_error("kmeans_finish: D=%d does not fit shared memory", D);
+    return SPALIGN_E_UNSUPPORTED;
+  }
+  TailArgs g;
+  int rc = fill_args(&g.a, plan, X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K);
+  if (rc) return rc;
+  g.a.ub = ub; g.a.lb = lb;
+  g.group_off = group_off; g.assign = assign; g.totals = totals; g.centers = centers;
+  g.iters = iters; g.status = status; g.cdelta = cdelta; g.n_iter = n_iter;
+  KM_DISPATCH(kmeans_tail_kernel, g, G);
+  return check_launch("kmeans_finish");
 }
 
 extern "C" int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off,

@@ -20,7 +20,7 @@ LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 
 # kernel launches per entry point (kept in sync with csrc/*.cu)
 _LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
-                    kmeans_sweep=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
+                    kmeans_sweep=1, kmeans_finish=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
                     refine=2, confusion2=1)
 
 
@@ -397,10 +397,11 @@ class KMeansLarge:
 
     TILE = 16           # rows per shared-memory tile of the main kernel variant
     TARGET_CHUNKS = 4 * 148
+    TAIL_ROWS = 2048    # groups up to this size finish in a persistent CTA each
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
-                 incremental=True, bounds=True):
+                 incremental=True, bounds=True, tail=True, tail_after=1):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -435,6 +436,17 @@ class KMeansLarge:
         self.fused = fused
         self.incremental = incremental
         self._full_done = False
+        # many small groups: after the first full iteration one persistent CTA per group runs
+        # the remaining iterations on its own (spalign_kmeans_finish), no per-iteration launch
+        sizes = np.diff(self.goff)
+        max_rows = int(sizes.max()) if self.G else 0
+        self.tail = (tail and self.ub is not None and allreduce is None and
+                     chunks_per_group is None and
+                     (max_rows <= self.TAIL_ROWS or
+                      (max_rows <= 8 * self.TAIL_ROWS and self.G >= 148)))
+        self.tail_after = tail_after
+        if self.tail:
+            self.goff_dev = torch.from_numpy(self.goff).to(dev, non_blocking=True)
         self._lib = _lib.load()
         self._init_done = False
 
@@ -536,6 +548,17 @@ class KMeansLarge:
         count, used by tests)."""
         if not self._init_done:
             self.init_centers()
+        if self.tail and self.n_iter > 0:
+            for _ in range(min(self.tail_after, self.n_iter)):
+                self._sweep(1)
+            check(self._lib.spalign_kmeans_finish(
+                _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
+                self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K,
+                _ptr(self.goff_dev), self.G, self.n_iter, _ptr(self.assign), _ptr(self.totals),
+                _ptr(self.centers), _ptr(self.iters), _ptr(self.status), _ptr(self.ub),
+                _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_finish')
+            _count('kmeans_finish')
+            return KMeansResult(self.assign, self.iters, self.status, self.centers)
         done = 0
         nxt = min(first_poll, self.n_iter)
         pending = None
