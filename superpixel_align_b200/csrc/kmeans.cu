@@ -31,15 +31,28 @@ namespace {
 
 constexpr int KM_THREADS = 256;
 constexpr int KMAX = 8;
+constexpr int KM_NBAR = 2 + 2 * (KM_THREADS / 32);
 constexpr int ACT_MAX = 1024;  // rows per chunk up to which stable rows are compacted away
+// entries of the active-row list: chunk-relative row index plus, once the row has been screened,
+// its new / old cluster and flags
+constexpr int ACT_ROW = 0xffff;
+constexpr int ACT_NEW_SHIFT = 16, ACT_OLD_SHIFT = 20;
+constexpr int ACT_CHG = 1 << 24;   // the row changed cluster
+constexpr int ACT_AMB = 1 << 25;   // the row needs the exact float64 pass
 
 // diagnostics: [0] rows screened, [1] rows sent to the exact float64 pass
 __device__ unsigned long long g_km_stats[2];
 #ifdef KM_PROFILE
 __device__ unsigned long long g_km_prof[8];
+__device__ unsigned long long g_km_prof2[8];
+__device__ unsigned long long g_km_prof3[8];
+#define KM_TICK3(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof3__[i] += now__ - last3__; last3__ = now__; } } while (0)
+#define KM_TICK2(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof2__[i] += now__ - last2__; last2__ = now__; } } while (0)
 #define KM_TICK(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof__[i] += now__ - last__; last__ = now__; } } while (0)
 #else
 #define KM_TICK(i) do {} while (0)
+#define KM_TICK2(i) do {} while (0)
+#define KM_TICK3(i) do {} while (0)
 #endif
 
 struct KmArgs {
@@ -53,6 +66,7 @@ struct KmArgs {
   int D;              // columns incl. virtual ones
   int Dr;             // stored columns
   int Dc;             // centre row stride (elements)
+  int Dm;             // leading stored columns screened in fp32 (multiple of 4)
   int K;
   int srow;           // shared-memory row stride in bytes
   int copy16;         // 16-byte chunks copied per row
@@ -76,12 +90,12 @@ struct KmSmem {
   double* extra;    // [KMAX][4] sum(omega), count, sum(omega*px), sum(omega*py)
   float* cnorm;     // [KMAX] upper bound of ||g_k|| (fp32 screening)
   double* hk;       // [KMAX] screening constants (hk[0]: magnitude scale)
-  int* order;       // [8 warps][32] tile rows grouped by cluster (per-warp copy)
+  unsigned short* order;  // [8 warps][32] tile rows grouped by cluster (per-warp copy)
   int* anew;        // [TR] new assignment per tile row (-1: undecided)
   int* amb;         // [TR] tile rows that need the exact float64 pass
   int* namb;        // [1]
   int* changed;     // [1]
-  unsigned long long* bar;  // [2] mbarrier per tile buffer
+  unsigned long long* bar;  // [2] mbarrier per tile buffer, then [8 warps][2] per-warp row buffers
   int* act;         // [ACT_MAX] chunk-relative indices of the rows that must be re-examined
   float* dk;        // [KMAX] centre drift of the last update (rounded up)
   float* dexcl;     // [KMAX] largest drift among the OTHER centres
@@ -113,8 +127,8 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += KMAX * sizeof(double);
   if (s) s->cnorm = reinterpret_cast<float*>(base + o);
   o += KMAX * sizeof(float);
-  if (s) s->order = reinterpret_cast<int*>(base + o);
-  o += 8 * 32 * sizeof(int);
+  if (s) s->order = reinterpret_cast<unsigned short*>(base + o);
+  o += 8 * 32 * sizeof(unsigned short);
   if (s) s->anew = reinterpret_cast<int*>(base + o);
   o += 32 * sizeof(int);
   if (s) s->amb = reinterpret_cast<int*>(base + o);
@@ -125,7 +139,7 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += sizeof(int);
   o = (o + 15) & ~(size_t)15;
   if (s) s->bar = reinterpret_cast<unsigned long long*>(base + o);
-  o += 2 * sizeof(unsigned long long);
+  o += KM_NBAR * sizeof(unsigned long long);
   if (s) s->act = reinterpret_cast<int*>(base + o);
   o += ACT_MAX * sizeof(int);
   if (s) s->dk = reinterpret_cast<float*>(base + o);
@@ -174,6 +188,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     if (spin > (1u << 28)) __trap();
 }
 
+__device__ __forceinline__ void km_init_barriers(const KmSmem& s) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KM_NBAR; ++i) mbar_init(s.bar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
 // warp 0 issues the tile: lane r copies row r with one bulk copy into the padded shared-memory
 // layout; lane 0 first posts the expected byte count of the whole tile
 template <typename XT>
@@ -187,7 +208,7 @@ __device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, unsigned 
     __syncwarp();
     for (int r = lane; r < nvalid; r += 32)
       bulk_g2s(buf + (size_t)r * a.srow,
-               src + ((size_t)(row0 + rows[r]) * a.ldx) * sizeof(XT), row_bytes, bar);
+               src + ((size_t)(row0 + (rows[r] & ACT_ROW)) * a.ldx) * sizeof(XT), row_bytes, bar);
     return;
   }
   if ((size_t)a.ldx * sizeof(XT) == (size_t)a.srow) {
@@ -245,6 +266,173 @@ __device__ __forceinline__ int np_argmin(const double (&d)[KT], int K) {
     }
   }
   return idx;
+}
+
+// fp32 screening, part 1: the warp's R shared-memory rows xw, xw + srow, ... against all
+// clusters.  Works on DIFFERENCES of squared distances to cluster 0.  With df = x - c_0:
+//   d_0^2 = sum df^2,   d_k^2 - d_0^2 = sum_d g_k[d]*df[d] + e_k,
+//   g_k = 2(c_0 - c_k),  e_k = ||c_0 - c_k||^2,
+// so a row costs one subtraction and K FFMA per element instead of 2K operations, and the
+// argmin over {0, delta_1, ...} is the argmin over the distances.  The first a.Dm columns go
+// through fp32; the few remaining stored columns (for the 514-column descriptors: the centroid
+// coordinates, the large-magnitude ones) and the virtual columns are added in float64 by
+// km_screen_decide.  Returns, in lane v < R*KT, the sum for row v / KT and cluster v % KT
+// (cluster 0: d_0^2, cluster k: the dot product with g_k), summed in a fixed order.
+template <int KT, int R>
+__device__ __forceinline__ float km_screen_partial(const KmArgs& a, const KmSmem s,
+                                                   const char* xw) {
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  constexpr int NV = R * KT;      // partial sums per lane
+  constexpr int LPV = 32 / NV;    // lanes that share the final sum of one value
+  static_assert(NV <= 32 && 32 % NV == 0, "R*KT must divide 32");
+  float a1[R][KT];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
+  const int main_d = a.Dm;
+  for (int d = lane * 4; d < main_d; d += 128) {
+    const float4 c0v = *reinterpret_cast<const float4*>(s.cen32 + d);
+    float4 df[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
+      df[r].x = xv.x - c0v.x; df[r].y = xv.y - c0v.y;
+      df[r].z = xv.z - c0v.z; df[r].w = xv.w - c0v.w;
+      a1[r][0] = fmaf(df[r].x, df[r].x, a1[r][0]);
+      a1[r][0] = fmaf(df[r].y, df[r].y, a1[r][0]);
+      a1[r][0] = fmaf(df[r].z, df[r].z, a1[r][0]);
+      a1[r][0] = fmaf(df[r].w, df[r].w, a1[r][0]);
+    }
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float4 gv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        a1[r][k] = fmaf(df[r].x, gv.x, a1[r][k]);
+        a1[r][k] = fmaf(df[r].y, gv.y, a1[r][k]);
+        a1[r][k] = fmaf(df[r].z, gv.z, a1[r][k]);
+        a1[r][k] = fmaf(df[r].w, gv.w, a1[r][k]);
+      }
+    }
+  }
+  // warp-level sum of the NV values through a padded shared-memory transpose (fixed order)
+  float* pw = reinterpret_cast<float*>(s.part) + (size_t)wq * (NV * 33);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < KT; ++k) pw[(r * KT + k) * 33 + lane] = a1[r][k];
+  __syncwarp();
+  float tot = 0.f;
+  {
+    const int v = lane % NV, seg = lane / NV;
+    const float* src = pw + v * 33 + seg * (32 / LPV);
+#pragma unroll
+    for (int j = 0; j < 32 / LPV; ++j) tot += src[j];
+#pragma unroll
+    for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  }
+  return tot;
+}
+
+// fp32 screening, part 2: one lane decides one row from its KT screening sums F, the row's
+// stored columns past a.Dm (xt, at most KM_NTAIL) and its global row index gr.  Returns the
+// proven nearest cluster, or -1 when the rounding-error bound cannot separate the candidates
+// (the row then needs the exact float64 pass).  Decided rows refresh their Hamerly bounds.
+// Rounding of the fp32 part (u = 2^-24): c_0 and g are rounded once, df once, and the
+// accumulation depth is below 100 (4 per 128 columns per lane, 16 in the transpose, 2
+// shuffles), so with d0 = ||df|| over the fp32 columns
+//   |dot_k - exact| <= (103u*d0 + u*||c_0||) * ||g_k||,
+//   |F_0  - exact| <= 102u*d0^2 + 2u*d0*||c_0|| + (u*||c_0||)^2.
+// We use eta = 2^-17 = 128u for all of them, norms rounded up, plus a floor of 2^-30 of the
+// magnitude scale so that float64-rounding-sized gaps stay undecided.  A row is decided only
+// when every other cluster stays strictly farther after both bounds; NaN/inf never decide.
+constexpr int KM_NTAIL = 3;
+template <int KT>
+__device__ __forceinline__ int km_screen_decide(const KmArgs& a, const KmSmem s,
+                                                const float (&F)[KT],
+                                                const float (&xt)[KM_NTAIL], int64_t gr,
+                                                bool bounds) {
+  const int K = a.K, Dr = a.Dr;
+  double delta[KT];
+  delta[0] = 0.0;
+#pragma unroll
+  for (int k = 1; k < KT; ++k) delta[k] = (double)F[k] - s.hk[k];
+  // stored columns past a.Dm and the virtual columns, exactly, in float64
+  double tail0 = 0.0;   // their share of d_0^2
+  auto add_col = [&](double xv, int d) {
+    const double c0 = s.cen[d];
+    tail0 = fma(xv - c0, xv - c0, tail0);
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      if (k < K) {
+        const double ck = s.cen[(size_t)k * a.Dc + d];
+        delta[k] = fma(c0 - ck, 2.0 * xv - c0 - ck, delta[k]);
+      }
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < KM_NTAIL; ++c)
+    if (a.Dm + c < Dr) add_col((double)xt[c], a.Dm + c);
+  if (a.pos_mode) {
+    double px, py;
+    virtual_pos(a, gr, &px, &py);
+    add_col(px, Dr);
+    add_col(py, Dr + 1);
+  }
+  int j = 0;
+  double best = 0.0;
+#pragma unroll
+  for (int k = 1; k < KT; ++k)
+    if (delta[k] < best) { best = delta[k]; j = k; }
+  const float d0 = sqrtf(F[0]) * 1.0001f;
+  const float c0n = s.cnorm[0];
+  const double D0 = (double)F[0] + tail0;                       // d_0^2, all columns
+  const double E0 = 7.63e-6 * ((double)F[0] + 2.0 * (double)(d0 * c0n)) +
+                    (double)(c0n * 6.0e-8f) * (double)(c0n * 6.0e-8f);
+  const double floor_ = 9.4e-10 * (D0 + s.hk[0]);               // 2^-30 * scale
+  double B[KT];
+  B[0] = 0.0;
+#pragma unroll
+  for (int k = 1; k < KT; ++k) B[k] = 7.63e-6 * (double)((d0 + c0n) * s.cnorm[k]);
+  double Bj = 0.0;
+#pragma unroll
+  for (int k = 1; k < KT; ++k)
+    if (k == j) Bj = B[k];
+  bool certain = (best == best) && (F[0] < 3.0e38f) && (j < K);
+  double second = 1.0e300;   // smallest provable squared distance to another centre
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    if (k != j) {
+      certain = certain && (delta[k] - best > B[k] + Bj + floor_);
+      second = fmin(second, D0 + delta[k] - E0 - B[k]);
+    }
+  }
+  if (!certain) return -1;
+  if (bounds) {
+    // bounds on the distances: squared bounds rounded outwards to fp32, then directed sqrt
+    const float u2 = __double2float_ru(fmax(D0 + best + E0 + Bj, 0.0));
+    const float l2 = __double2float_rd(fmax(second, 0.0));
+    a.ub[gr] = __fmul_ru(__fsqrt_ru(u2), 1.000001f);
+    a.lb[gr] = __fmul_rd(__fsqrt_rd(l2), 0.999999f);
+  }
+  return j;
+}
+
+// stage the warp's screening sums (lane v < R*KT) and its rows' tail columns for the lanes
+// that will decide the rows: stF[(slot0 + r)*KT + k], stX[(slot0 + r)*KM_NTAIL + c]
+template <int KT, int R>
+__device__ __forceinline__ void km_screen_stage(const KmArgs& a, const char* xw, float tot,
+                                                float* stF, float* stX, int slot0) {
+  const int lane = threadIdx.x & 31;
+  if (lane < R * KT) stF[slot0 * KT + lane] = tot;
+  const int ntail = a.Dr - a.Dm;
+  if (lane < R * ntail) {
+    const int r = lane / ntail, c = lane - r * ntail;
+    stX[(slot0 + r) * KM_NTAIL + c] =
+        reinterpret_cast<const float*>(xw + (size_t)r * a.srow)[a.Dm + c];
+  }
 }
 
 // Hamerly bounds pass over the rows [row_begin, row_begin + N) of a chunk (mode 2): shift every
@@ -333,7 +521,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   if (ntiles > 0 && t < 32)
     issue_tile<XT>(a, s.buf0 + (size_t)(tile_base & 1) * s.tile_bytes, s.bar + (tile_base & 1),
                    row_begin, min(TR, nrows), compact ? s.act : nullptr);
-#define KM_ROW(r) (compact ? row_begin + (int64_t)s.act[tb + (r)] : row_begin + (int64_t)(tb + (r)))
+#define KM_ROW(r) (compact ? row_begin + (int64_t)(s.act[tb + (r)] & ACT_ROW) : row_begin + (int64_t)(tb + (r)))
 #ifdef KM_PROFILE
   long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long last__ = clock64();
@@ -342,7 +530,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   const bool fastcvt = kF32 && mode != 0 && xflag != nullptr && *xflag == 0;
   bool saw_special = false;
   const int lane_ = t & 31, wq_ = t >> 5;
-  int* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
+  unsigned short* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
   double* my_om = s.om + wq_ * 32;
   for (int ti = 0; ti < ntiles; ++ti) {
     const int tb = ti * TR;                          // index of the tile's first row in the
@@ -355,8 +543,15 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     int pre_a = -1;
     double pre_w = 0.0;
     const int prow = lane_ & (TR - 1);
+    int pre_n = -1;  // mode 3: new cluster, decided by the screening pass
     if (lane_ < 2 * TR && lane_ < 32 && prow < nvalid) {
-      pre_a = assign[KM_ROW(prow)];
+      if (mode == 3) {
+        const int e = s.act[tb + prow];
+        pre_a = (e >> ACT_OLD_SHIFT) & 15;
+        pre_n = (e >> ACT_NEW_SHIFT) & 15;
+      } else {
+        pre_a = assign[KM_ROW(prow)];
+      }
       if (mode != 0) pre_w = a.w[KM_ROW(prow)];
     }
     __syncthreads();  // (A) all warps are past phase 2 of tile ti-1: its buffer is free
@@ -370,147 +565,28 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     const char* tile = s.buf0 + (size_t)(gt & 1) * s.tile_bytes;
     KM_TICK(1);
 
-    if (mode != 0) {
+    if (mode == 1 || mode == 2) {
       if (kF32) {
-        // ---- phase 1 (fp32 screening): one warp owns R rows, lanes stride the columns ----
-        constexpr int NV = R * KT;      // partial sums per lane
-        constexpr int LPV = 32 / NV;    // lanes that share the final sum of one value
-        static_assert(NV <= 32 && 32 % NV == 0, "R*KT must divide 32");
-        const int lane = t & 31, wq = t >> 5;
-        const int rbase = wq * R;
-        float a1[R][KT];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
-        // Screening works on DIFFERENCES of squared distances to cluster 0.  With df = x - c_0:
-        //   d_0^2 = sum df^2,   d_k^2 - d_0^2 = sum_d g_k[d]*df[d] + e_k,
-        //   g_k = 2(c_0 - c_k),  e_k = ||c_0 - c_k||^2,
-        // so a row costs one subtraction and K FFMA per element instead of 2K operations, and
-        // the argmin over {0, delta_1, ...} is the argmin over the distances.  The first
-        // main_d = Dr & ~127 columns go through fp32; the few remaining stored columns (for the
-        // 514-column descriptors: the centroid coordinates, the large-magnitude ones) and the
-        // virtual columns are added in float64 by the lane that finishes the row.
-        const int main_d = Dr & ~127;
-        const char* xw = tile + (size_t)rbase * a.srow;
-        for (int d = lane * 4; d < main_d; d += 128) {
-          const float4 c0v = *reinterpret_cast<const float4*>(s.cen32 + d);
-          float4 df[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 xv =
-                *reinterpret_cast<const float4*>(xw + (size_t)r * a.srow + (size_t)d * 4);
-            df[r].x = xv.x - c0v.x; df[r].y = xv.y - c0v.y;
-            df[r].z = xv.z - c0v.z; df[r].w = xv.w - c0v.w;
-            a1[r][0] = fmaf(df[r].x, df[r].x, a1[r][0]);
-            a1[r][0] = fmaf(df[r].y, df[r].y, a1[r][0]);
-            a1[r][0] = fmaf(df[r].z, df[r].z, a1[r][0]);
-            a1[r][0] = fmaf(df[r].w, df[r].w, a1[r][0]);
-          }
-#pragma unroll
-          for (int k = 1; k < KT; ++k) {
-            const float4 gv = *reinterpret_cast<const float4*>(s.cen32 + (size_t)k * a.Dc + d);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              a1[r][k] = fmaf(df[r].x, gv.x, a1[r][k]);
-              a1[r][k] = fmaf(df[r].y, gv.y, a1[r][k]);
-              a1[r][k] = fmaf(df[r].z, gv.z, a1[r][k]);
-              a1[r][k] = fmaf(df[r].w, gv.w, a1[r][k]);
-            }
-          }
-        }
-        // warp-level sum of the NV values through a padded shared-memory transpose (fixed order)
-        float* pw = reinterpret_cast<float*>(s.part) + (size_t)wq * (NV * 33);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < KT; ++k) pw[(r * KT + k) * 33 + lane] = a1[r][k];
-        __syncwarp();
-        float tot = 0.f;
+        // ---- phase 1 (fp32 screening): one warp owns R rows, lanes stride the columns; the
+        // sums are staged and warp 0 decides all rows of the tile at once ----
+        __shared__ float stF[32 * KT];
+        __shared__ float stX[32 * KM_NTAIL];
         {
-          const int v = lane % NV, seg = lane / NV;
-          const float* src = pw + v * 33 + seg * (32 / LPV);
-#pragma unroll
-          for (int j = 0; j < 32 / LPV; ++j) tot += src[j];
-#pragma unroll
-          for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+          const int rbase = (t >> 5) * R;
+          const char* xw = tile + (size_t)rbase * a.srow;
+          const float tot = km_screen_partial<KT, R>(a, s, xw);
+          km_screen_stage<KT, R>(a, xw, tot, stF, stX, rbase);
         }
-        // lane r (< R) finishes row rbase + r.  Rounding of the fp32 part (u = 2^-24): c_0 and
-        // g are rounded once, df once, and the accumulation depth is <= 34 (16 per lane, 16 in
-        // the transpose, 2 shuffles), so with d0 = ||df|| over the fp32 columns
-        //   |dot_k - exact| <= (37u*d0 + u*||c_0||) * ||g_k||,
-        //   |F_0  - exact| <= 36u*d0^2 + 2u*d0*||c_0|| + (u*||c_0||)^2.
-        // We use eta = 2^-17 (3.5x) for all of them, norms rounded up, plus a floor of 2^-30 of
-        // the magnitude scale so that float64-rounding-sized gaps stay undecided.  A row is
-        // decided only when every other cluster stays strictly farther after both bounds;
-        // NaN/inf never decide.  Decided rows also refresh their Hamerly bounds.
-        float F[KT];
+        __syncthreads();
+        if (t < nvalid) {
+          float F[KT], xt[KM_NTAIL];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) F[k] = __shfl_sync(0xffffffffu, tot, (lane % R) * KT + k);
-        if (lane < R && rbase + lane < nvalid) {
-          const int rr = rbase + lane;
-          double delta[KT];
-          delta[0] = 0.0;
+          for (int k = 0; k < KT; ++k) F[k] = stF[t * KT + k];
 #pragma unroll
-          for (int k = 1; k < KT; ++k) delta[k] = (double)F[k] - s.hk[k];
-          // stored columns past main_d and the virtual columns, exactly, in float64
-          double tail0 = 0.0;   // their share of d_0^2
-          const float* xrow = reinterpret_cast<const float*>(tile + (size_t)rr * a.srow);
-          for (int d = main_d; d < a.D; ++d) {
-            double xv;
-            if (d < Dr) {
-              xv = (double)xrow[d];
-            } else {
-              double px, py;
-              virtual_pos(a, KM_ROW(rr), &px, &py);
-              xv = d == Dr ? px : py;
-            }
-            const double c0 = s.cen[d];
-            tail0 = fma(xv - c0, xv - c0, tail0);
-#pragma unroll
-            for (int k = 1; k < KT; ++k) {
-              if (k < K) {
-                const double ck = s.cen[(size_t)k * a.Dc + d];
-                delta[k] = fma(c0 - ck, 2.0 * xv - c0 - ck, delta[k]);
-              }
-            }
-          }
-          int j = 0;
-          double best = 0.0;
-#pragma unroll
-          for (int k = 1; k < KT; ++k)
-            if (delta[k] < best) { best = delta[k]; j = k; }
-          const float d0 = sqrtf(F[0]) * 1.0001f;
-          const float c0n = s.cnorm[0];
-          const double D0 = (double)F[0] + tail0;                       // d_0^2, all columns
-          const double E0 = 7.63e-6 * ((double)F[0] + 2.0 * (double)(d0 * c0n)) +
-                            (double)(c0n * 6.0e-8f) * (double)(c0n * 6.0e-8f);
-          const double floor_ = 9.4e-10 * (D0 + s.hk[0]);               // 2^-30 * scale
-          double B[KT];
-          B[0] = 0.0;
-#pragma unroll
-          for (int k = 1; k < KT; ++k) B[k] = 7.63e-6 * (double)((d0 + c0n) * s.cnorm[k]);
-          double Bj = 0.0;
-#pragma unroll
-          for (int k = 1; k < KT; ++k)
-            if (k == j) Bj = B[k];
-          bool certain = (best == best) && (F[0] < 3.0e38f) && (j < K);
-          double second = 1.0e300;   // smallest provable squared distance to another centre
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            if (k != j) {
-              certain = certain && (delta[k] - best > B[k] + Bj + floor_);
-              second = fmin(second, D0 + delta[k] - E0 - B[k]);
-            }
-          }
-          s.anew[rr] = certain ? j : -1;
-          if (!certain) {
-            s.amb[atomicAdd(s.namb, 1)] = rr;
-          } else if (bounds) {
-            const int64_t gr = KM_ROW(rr);
-            a.ub[gr] = __fmul_ru(__double2float_ru(sqrt(fmax(D0 + best + E0 + Bj, 0.0))), 1.000001f);
-            a.lb[gr] = __fmul_rd(__double2float_rd(sqrt(fmax(second, 0.0))), 0.999999f);
-          }
+          for (int c = 0; c < KM_NTAIL; ++c) xt[c] = stX[t * KM_NTAIL + c];
+          const int j = km_screen_decide<KT>(a, s, F, xt, KM_ROW(t), bounds);
+          s.anew[t] = j;
+          if (j < 0) s.amb[atomicAdd(s.namb, 1)] = t;
         }
         __syncthreads();
 
@@ -650,7 +726,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
           a_new = pre_a;
           om = 1.0;
         } else {
-          const int an = s.anew[prow];
+          const int an = mode == 3 ? pre_n : s.anew[prow];
           chg = an != pre_a;
           if (mode == 1) {                       // full sums: every row, new cluster
             valid = half == 0;
@@ -664,7 +740,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
           }
         }
       }
-      const int an_row = (mode != 0 && in_tile) ? s.anew[prow] : pre_a;
+      const int an_row = (mode != 0 && mode != 3 && in_tile) ? s.anew[prow] : pre_a;
       int pos = 0, base = 0;
       const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -678,13 +754,13 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       }
       startk[KT] = base;
       if (valid && a_new >= 0 && a_new < K) {
-        my_order[pos] = prow | (half << 8);      // bit 8: the entry removes the row
+        my_order[pos] = (unsigned short)(prow | (half << 8));  // bit 8: the entry removes the row
         my_om[pos] = om;
       }
       const unsigned cm = __ballot_sync(0xffffffffu, chg != 0 && half == 0);
       __syncwarp();
       if (wq_ == 0) {  // warp 0 owns the assignment write-back
-        if (chg && half == 0) assign[KM_ROW(prow)] = an_row;
+        if (chg && half == 0 && mode != 3) assign[KM_ROW(prow)] = an_row;
         if (lane == 0 && cm) *s.changed += __popc(cm);
       }
       if (wq_ == 1) {  // warp 1 owns the per-cluster scalars
@@ -765,7 +841,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   if (kF32 && mode == 0 && xflag != nullptr && saw_special) atomicOr(xflag, 1);
   __syncthreads();
 #ifdef KM_PROFILE
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && compact) {  // compacted mode-2 sweeps only
     for (int i = 0; i < 6; ++i) atomicAdd(&g_km_prof[i], (unsigned long long)prof__[i]);
     atomicAdd(&g_km_prof[6], (unsigned long long)ntiles);
   }
@@ -779,6 +855,210 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     s.extra[lane_ * 4 + 3] = e_y;
   }
   __syncthreads();
+}
+
+// Mode-2 sweep over the `na` rows listed in s.act (the rows a bounds pass left active).
+//   1. screening, warp-independent: every warp gathers its own R rows at a time into a private
+//      double buffer (bulk copies on its own mbarriers), screens them and records the outcome
+//      in the row's list entry -- no block barrier, so the eight warps overlap each other's
+//      copy, FFMA and finalisation latency;
+//   2. exact float64 pass, whole block, for the (rare) rows the screening could not prove;
+//   3. the rows that changed cluster are compacted (in row order) and handed to km_sweep in
+//      mode 3, which moves them between the running sums exactly as mode 2 does.
+// Same decisions, same summation order as the tiled mode-2 sweep.
+template <int KT, int NS2, int R>
+__device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
+                                                int64_t row_begin, int na,
+                                                int32_t* __restrict__ assign,
+                                                double (&acc)[KT][NS2][2], unsigned& tile_base,
+                                                unsigned& wtile) {
+  const int t = threadIdx.x, lane = t & 31, wq = t >> 5;
+  const int K = a.K, Dr = a.Dr;
+  const unsigned row_bytes = (unsigned)a.copy16 * 16u;
+  const char* Xb = reinterpret_cast<const char*>(a.X);
+  char* wbuf = s.buf0 + (size_t)wq * 2 * R * a.srow;          // this warp's two R-row buffers
+  unsigned long long* wbar = s.bar + 2 + wq * 2;
+  const int nsets = (na + R - 1) / R;                          // sets of R list entries
+  constexpr int BR = 16;                                       // rows per decision batch
+  constexpr int SPB = BR / R;
+  __shared__ float stF[KM_THREADS / 32][BR * KT];
+  __shared__ float stX[KM_THREADS / 32][BR * KM_NTAIL];
+  __shared__ signed char stA[KM_THREADS / 32][BR];             // assignment before the sweep
+  const int my_n = nsets > wq ? (nsets - wq + 7) / 8 : 0;      // sets wq, wq + 8, ...
+  auto issue = [&](int set, unsigned gt) {
+    const int base = set * R;
+    const int nv = min(R, na - base);
+    char* dst = wbuf + (size_t)(gt & 1) * R * a.srow;
+    if (lane == 0) mbar_expect_tx(wbar + (gt & 1), row_bytes * (unsigned)nv);
+    __syncwarp();
+    if (lane < nv)
+      bulk_g2s(dst + (size_t)lane * a.srow,
+               Xb + ((size_t)(row_begin + (s.act[base + lane] & ACT_ROW)) * a.ldx) * sizeof(float),
+               row_bytes, wbar + (gt & 1));
+  };
+#ifdef KM_PROFILE
+  long long prof3__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long last3__ = clock64();
+#endif
+  if (my_n > 0) issue(wq, wtile);
+  for (int i = 0; i < my_n; ++i) {
+    const int set = wq + 8 * i;
+    const unsigned gt = wtile + (unsigned)i;
+    __syncwarp();  // every lane is done reading the buffer the next copy overwrites
+    if (i + 1 < my_n) issue(set + 8, gt + 1);
+    // the row's current assignment travels with it (loaded while the copy is in flight)
+    int old_a = 0;
+    {
+      const int pos_l = (wq + 8 * i) * R + lane;
+      if (lane < R && pos_l < na) old_a = assign[row_begin + (s.act[pos_l] & ACT_ROW)];
+    }
+    KM_TICK3(0);
+    mbar_wait(wbar + (gt & 1), (gt >> 1) & 1);
+    KM_TICK3(1);
+    const char* xw = wbuf + (size_t)(gt & 1) * R * a.srow;
+    const float tot = km_screen_partial<KT, R>(a, s, xw);
+    KM_TICK3(2);
+    const int sb = i % SPB;  // set within the batch
+    km_screen_stage<KT, R>(a, xw, tot, stF[wq], stX[wq], sb * R);
+    if (lane < R) stA[wq][sb * R + lane] = (signed char)old_a;
+    if (sb == SPB - 1 || i == my_n - 1) {
+      // decide the batch: lane q takes the q-th staged row
+      __syncwarp();
+      const int i0 = i - sb;
+      const int pos = (wq + 8 * (i0 + lane / R)) * R + lane % R;   // list position of the row
+      if (lane < (sb + 1) * R && pos < na) {
+        const int64_t gr = row_begin + (s.act[pos] & ACT_ROW);
+        const int old = stA[wq][lane];
+        float F[KT], xt[KM_NTAIL];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) F[k] = stF[wq][lane * KT + k];
+#pragma unroll
+        for (int c = 0; c < KM_NTAIL; ++c) xt[c] = stX[wq][lane * KM_NTAIL + c];
+        const int j = km_screen_decide<KT>(a, s, F, xt, gr, true);
+        int e = s.act[pos] & ACT_ROW;
+        if (j < 0) {
+          e |= ACT_AMB;
+        } else if (j != old) {
+          e |= ACT_CHG | (j << ACT_NEW_SHIFT) | ((old & 15) << ACT_OLD_SHIFT);
+          assign[gr] = j;
+        }
+        s.act[pos] = e;
+      }
+      __syncwarp();
+    }
+    KM_TICK3(3);
+  }
+#ifdef KM_PROFILE
+  prof3__[7] += my_n;
+#endif
+  KM_TICK3(0);
+  wtile += (unsigned)my_n;
+  if (t == 0) atomicAdd(&g_km_stats[0], (unsigned long long)na);
+  // ---- exact pass ----
+  int any = 0;
+  __syncthreads();
+  for (int p = t; p < na; p += KM_THREADS) any |= (s.act[p] & ACT_AMB) != 0;
+  any = __syncthreads_or(any);
+  if (any) {
+    for (int p = 0; p < na; ++p) {
+      const int e = s.act[p];
+      if (!(e & ACT_AMB)) continue;  // uniform: every thread reads the same entry
+      const int64_t gr = row_begin + (e & ACT_ROW);
+      const float* xr = reinterpret_cast<const float*>(Xb + (size_t)gr * a.ldx * sizeof(float));
+      double pd[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) pd[k] = 0.0;
+      for (int d = t; d < Dr; d += KM_THREADS) {
+        const double xv = (double)xr[d];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (k < K) {
+            const double df = xv - s.cen[(size_t)k * a.Dc + d];
+            pd[k] = fma(df, df, pd[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pd[k] += __shfl_xor_sync(0xffffffffu, pd[k], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) s.red[(size_t)wq * KMAX + k] = pd[k];
+      }
+      __syncthreads();
+      if (t == 0) {
+        double dd[KT];
+        double px = 0.0, py = 0.0;
+        if (a.pos_mode) virtual_pos(a, gr, &px, &py);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          double sum = 0.0;
+          if (k < K) {
+            for (int q = 0; q < KM_THREADS / 32; ++q) sum += s.red[(size_t)q * KMAX + k];
+            if (a.pos_mode) {
+              const double dx = px - s.cen[(size_t)k * a.Dc + Dr];
+              const double dy = py - s.cen[(size_t)k * a.Dc + Dr + 1];
+              sum = fma(dx, dx, sum);
+              sum = fma(dy, dy, sum);
+            }
+          }
+          dd[k] = sqrt(sum);
+        }
+        const int jj = np_argmin<KT>(dd, K);
+        double sec = 1.0e300;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < K && k != jj) sec = fmin(sec, dd[k]);
+        const bool okd = dd[jj] == dd[jj] && sec == sec;
+        a.ub[gr] = okd ? __fmul_ru(__double2float_ru(dd[jj]), 1.000001f)
+                       : __int_as_float(0x7f800000);
+        a.lb[gr] = okd ? __fmul_rd(__double2float_rd(sec), 0.999999f) : 0.f;
+        const int old = assign[gr];
+        int ne = e & ACT_ROW;
+        if (jj != old) {
+          ne |= ACT_CHG | (jj << ACT_NEW_SHIFT) | ((old & 15) << ACT_OLD_SHIFT);
+          assign[gr] = jj;
+        }
+        s.act[p] = ne;
+        atomicAdd(&g_km_stats[1], 1ULL);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- changed rows, compacted in place in list order ----
+  __shared__ int wcnt2[KM_THREADS / 32];
+  __shared__ int nchg_s;
+  if (t == 0) nchg_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < na; i0 += KM_THREADS) {
+    const int i = i0 + t;
+    const int e = i < na ? s.act[i] : 0;
+    const bool c = (e & ACT_CHG) != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    if (lane == 0) wcnt2[wq] = __popc(m);
+    __syncthreads();
+    int before = nchg_s;
+    for (int q = 0; q < wq; ++q) before += wcnt2[q];
+    if (c) s.act[before + __popc(m & ((1u << lane) - 1u))] = e;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int q = 0; q < KM_THREADS / 32; ++q) tot += wcnt2[q];
+      nchg_s += tot;
+    }
+    __syncthreads();
+  }
+  const int nchg = nchg_s;
+  KM_TICK3(4);
+#ifdef KM_PROFILE
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_km_prof3[i], (unsigned long long)prof3__[i]);
+  }
+#endif
+  km_sweep<float, KT, NS2, R>(a, s, row_begin, row_begin + ACT_MAX, 3, assign, acc, tile_base,
+                              nullptr, nchg);
 }
 
 template <int KT, int NS2>
@@ -828,7 +1108,7 @@ __device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) 
   // float64 floor).  Clusters K..KT-1 of the unrolled kernel get g = 0 and a huge delta: they
   // never win and never make a row undecided.
   const int t = threadIdx.x;
-  const int main_d = a.Dr & ~127;
+  const int main_d = a.Dm;
   for (int i = t; i < KT * a.Dc; i += KM_THREADS) {
     const int k = i / a.Dc, d = i - k * a.Dc;
     float g = 0.f;
@@ -904,11 +1184,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   unsigned tile_base = 0;
-  if (threadIdx.x == 0) {
-    mbar_init(s.bar + 0, 1);
-    mbar_init(s.bar + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  km_init_barriers(s);
   __syncthreads();
   km_sweep<XT, KT, NS2, R>(g.a, s, r0, r1, 0, g.assign, acc, tile_base);
   finalize_centers<KT, NS2>(g.a, s, acc);
@@ -1028,11 +1304,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   zero_acc<KT, NS2>(acc);
   if (t == 0) *s.changed = 0;
   unsigned tile_base = 0;
-  if (threadIdx.x == 0) {
-    mbar_init(s.bar + 0, 1);
-    mbar_init(s.bar + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  km_init_barriers(s);
   __syncthreads();
   // mode 2 with Hamerly bounds: find the rows that must be re-examined before anything else;
   // a chunk without such rows only reports zeros
@@ -1051,7 +1323,16 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
       __syncthreads();
       if (sizeof(XT) == 4) prepare_screen<KT>(g.a, s);
     }
-    km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag, nrows_in);
+    if constexpr (sizeof(XT) == 4) {
+      if (nrows_in > 0) {
+        unsigned wtile = 0;
+        km_sweep_sparse<KT, NS2, R>(g.a, s, rb, nrows_in, g.assign, acc, tile_base, wtile);
+      } else {
+        km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
+      }
+    } else {
+      km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
+    }
   } else if (t < K) {
     s.extra[t * 4 + 0] = s.extra[t * 4 + 1] = s.extra[t * 4 + 2] = s.extra[t * 4 + 3] = 0.0;
   }
@@ -1149,11 +1430,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   double* cg = g.centers + (size_t)grp * K * D;
   double* cd = g.cdelta + (size_t)grp * K;
   __shared__ double xs[KMAX * 4];
-  if (t == 0) {
-    mbar_init(s.bar + 0, 1);
-    mbar_init(s.bar + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  km_init_barriers(s);
   for (int i = t; i < K * D; i += KM_THREADS) {
     const int k = i / D, d = i - k * D;
     s.cen[(size_t)k * Dc + d] = cg[i];
@@ -1161,24 +1438,35 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   __syncthreads();
   int it = g.iters[grp];
   int status = SPALIGN_KM_ITER_CAP;
-  unsigned tile_base = 0;
+  unsigned tile_base = 0, wtile = 0;
   double acc[KT][NS2][2];
+#ifdef KM_PROFILE
+  long long prof2__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long last2__ = clock64();
+#endif
   while (it < g.n_iter) {
     zero_acc<KT, NS2>(acc);
     if (t == 0) *s.changed = 0;
     if (t < KMAX * 4) xs[t] = 0.0;
     prepare_screen<KT>(g.a, s);  // ends with a block barrier
+    KM_TICK2(0);
     for (int64_t rb = r0; rb < r1; rb += ACT_MAX) {
       const int n = (int)min((int64_t)ACT_MAX, r1 - rb);
       const int na = km_bounds_pass<KT>(g.a, s, rb, n, g.assign, cd);
+      KM_TICK2(1);
       if (na > 0) {
-        km_sweep<XT, KT, NS2, R>(g.a, s, rb, rb + n, 2, g.assign, acc, tile_base, nullptr, na);
+        if constexpr (sizeof(XT) == 4)
+          km_sweep_sparse<KT, NS2, R>(g.a, s, rb, na, g.assign, acc, tile_base, wtile);
         if (t < K * 4) xs[t] += s.extra[t];
         __syncthreads();
       }
+      KM_TICK2(2);
     }
     __syncthreads();
     ++it;
+#ifdef KM_PROFILE
+    prof2__[4] += 1;
+#endif
     if (*s.changed == 0) {  // assignment unchanged: centres stay
       status = SPALIGN_KM_CONVERGED;
       break;
@@ -1250,8 +1538,13 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       break;
     }
     __syncthreads();
+    KM_TICK2(3);
   }
   __syncthreads();
+#ifdef KM_PROFILE
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 5; ++i) atomicAdd(&g_km_prof2[i], (unsigned long long)prof2__[i]);
+#endif
   for (int i = t; i < K * D; i += KM_THREADS) {
     const int k = i / D, d = i - k * D;
     cg[i] = s.cen[(size_t)k * Dc + d];
@@ -1437,6 +1730,9 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   SPALIGN_REQUIRE(!pos_mode || (pos_w > 0 && pos_period > 0), "kmeans: bad pos_w/pos_period");
   a->X = X; a->ldx = ldx; a->pos_mode = pos_mode; a->pos_w = pos_w ? pos_w : 1;
   a->pos_period = pos_period ? pos_period : 1; a->pos_row0 = pos_row0; a->w = w;
+  // fp32-screened columns: all but the last <= 3 stored ones; a row length of 4n + 2 is taken
+  // as n*4 features plus the two centroid coordinates (large magnitudes, kept in float64)
+  a->Dm = (Dr % 4 == 2) ? Dr - 2 : (Dr & ~3);
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
   a->ub = nullptr; a->lb = nullptr;
@@ -1634,6 +1930,33 @@ extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
     }
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_km_prof, z, sizeof(z));
+    cudaMemcpyFromSymbol(p, g_km_prof2, sizeof(p));
+    if (p[4])
+      fprintf(stderr, "[km_profile] finish kernel: iterations=%llu  cycles/iteration (thread 0): prepare %.0f | bounds %.0f | sweep %.0f | update %.0f\n",
+              p[4], (double)p[0] / p[4], (double)p[1] / p[4], (double)p[2] / p[4], (double)p[3] / p[4]);
+    cudaMemcpyToSymbol(g_km_prof2, z, sizeof(z));
+    cudaMemcpyFromSymbol(p, g_km_prof3, sizeof(p));
+    if (p[7])
+      fprintf(stderr, "[km_profile] sparse sweep, warp 0: sets=%llu  cycles/set: issue %.0f | wait %.0f | partial %.0f | stage+decide %.0f ; exact+compaction per set %.0f\n",
+              p[7], (double)p[0] / p[7], (double)p[1] / p[7], (double)p[2] / p[7], (double)p[3] / p[7], (double)p[4] / p[7]);
+    cudaMemcpyToSymbol(g_km_prof3, z, sizeof(z));
+    {
+      Plan plan;
+      if (make_plan(SPALIGN_F32, 514, 514, 4, &plan, 16)) {
+        int nb_tail = 0, nb_sweep = 0;
+        set_smem(kmeans_tail_kernel<float, 4, 2, 2, 2>, plan.smem);
+        set_smem(kmeans_sweep_kernel<float, 4, 2, 2, 2>, plan.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_tail, kmeans_tail_kernel<float, 4, 2, 2, 2>,
+                                                      KM_THREADS, plan.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_sweep, kmeans_sweep_kernel<float, 4, 2, 2, 2>,
+                                                      KM_THREADS, plan.smem);
+        cudaFuncAttributes fa, fb;
+        cudaFuncGetAttributes(&fa, kmeans_tail_kernel<float, 4, 2, 2, 2>);
+        cudaFuncGetAttributes(&fb, kmeans_sweep_kernel<float, 4, 2, 2, 2>);
+        fprintf(stderr, "[km_profile] D=514 K=4: dynamic smem %zu B; CTAs/SM: finish kernel %d (static %zu B, %d regs), sweep kernel %d (static %zu B, %d regs)\n",
+                plan.smem, nb_tail, fa.sharedSizeBytes, fa.numRegs, nb_sweep, fb.sharedSizeBytes, fb.numRegs);
+      }
+    }
   }
 #endif
   unsigned long long h[2] = {0, 0};
