@@ -32,6 +32,11 @@ namespace {
 constexpr int KM_THREADS = 256;
 constexpr int KMAX = 8;
 constexpr int KM_NBAR = 2 + 2 * (KM_THREADS / 32);
+// columns outside the fp32 screening loop: <= 3 stored (KM_NTAIL) + 2 virtual
+constexpr int KM_NT = 5;
+// fz layout: gt[KMAX][KM_NT] | c0t[KM_NT] | ek[KMAX] | ak[KMAX] | c0tn
+constexpr int FZ_GT = 0, FZ_C0T = KMAX * KM_NT, FZ_EK = FZ_C0T + KM_NT, FZ_AK = FZ_EK + KMAX,
+              FZ_C0TN = FZ_AK + KMAX, KM_FZ = FZ_C0TN + 3;
 constexpr int ACT_MAX = 1024;  // rows per chunk up to which stable rows are compacted away
 // entries of the active-row list: chunk-relative row index plus, once the row has been screened,
 // its new / old cluster and flags
@@ -46,6 +51,7 @@ __device__ unsigned long long g_km_stats[2];
 __device__ unsigned long long g_km_prof[8];
 __device__ unsigned long long g_km_prof2[8];
 __device__ unsigned long long g_km_prof3[8];
+__device__ unsigned long long g_km_slow;
 #define KM_TICK3(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof3__[i] += now__ - last3__; last3__ = now__; } } while (0)
 #define KM_TICK2(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof2__[i] += now__ - last2__; last2__ = now__; } } while (0)
 #define KM_TICK(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof__[i] += now__ - last__; last__ = now__; } } while (0)
@@ -100,6 +106,7 @@ struct KmSmem {
   float* dk;        // [KMAX] centre drift of the last update (rounded up)
   float* dexcl;     // [KMAX] largest drift among the OTHER centres
   int* nact;        // [1]
+  float* fz;        // [KM_FZ] fp32 constants of the fast decision path (see prepare_screen)
 };
 
 __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
@@ -148,6 +155,8 @@ __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int sr
   o += KMAX * sizeof(float);
   if (s) s->nact = reinterpret_cast<int*>(base + o);
   o += 4 * sizeof(int);
+  if (s) s->fz = reinterpret_cast<float*>(base + o);
+  o += KM_FZ * sizeof(float);
   return o + 64;
 }
 
@@ -355,6 +364,94 @@ __device__ __forceinline__ int km_screen_decide(const KmArgs& a, const KmSmem s,
                                                 const float (&xt)[KM_NTAIL], int64_t gr,
                                                 bool bounds) {
   const int K = a.K, Dr = a.Dr;
+  {
+    // ---- fast path, all fp32, every rounding accounted for ----
+    // With x'_c = x_c - c0_c over the tail columns, delta_k = d_k^2 - d_0^2 is
+    //   F[k] + e_k + sum_c gt[k][c] x'_c,          tail share of d_0^2: sum_c x'_c^2.
+    // Evaluated in fp32 the deviation from the float64 evaluation below is at most
+    //   eps_k = 2^-20 M_k + 2^-23 ak[k],   M_k = |F[k]| + |e_k| + sum_c |gt[k][c] x'_c|
+    // (roundings of c0_c, gt, e_k and of the <= 7 additions), so a gap that exceeds the
+    // screening bounds by eps_k + eps_j as well is also a gap of the float64 test, with the
+    // same winner.  Rows that fail here take the float64 path; NaN/inf fail every comparison.
+    float xp[KM_NT];
+    float tail0 = 0.f;
+#pragma unroll
+    for (int c = 0; c < KM_NT; ++c) xp[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KM_NTAIL; ++c)
+      if (a.Dm + c < Dr) xp[c] = xt[c] - s.fz[FZ_C0T + c];
+    if (a.pos_mode) {
+      double px, py;
+      virtual_pos(a, gr, &px, &py);
+      const int c = Dr - a.Dm;
+#pragma unroll
+      for (int q = 0; q < KM_NTAIL + 1; ++q) {
+        if (q == c) {
+          xp[q] = (float)px - s.fz[FZ_C0T + q];
+          xp[q + 1] = (float)py - s.fz[FZ_C0T + q + 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < KM_NT; ++c) tail0 = fmaf(xp[c], xp[c], tail0);
+    float dl[KT], ep[KT], Bf[KT];
+    dl[0] = 0.f; ep[0] = 0.f; Bf[0] = 0.f;
+    const float d0 = sqrtf(F[0]) * 1.0001f;
+    const float c0n = s.cnorm[0];
+#pragma unroll
+    for (int k = 1; k < KT; ++k) {
+      const float ek = s.fz[FZ_EK + k];
+      float v = F[k] + ek, m = fabsf(F[k]) + fabsf(ek);
+#pragma unroll
+      for (int c = 0; c < KM_NT; ++c) {
+        const float p = s.fz[FZ_GT + k * KM_NT + c] * xp[c];
+        v += p;
+        m += fabsf(p);
+      }
+      dl[k] = k < K ? v : 3.0e38f;
+      ep[k] = k < K ? 9.6e-7f * m + 1.2e-7f * s.fz[FZ_AK + k] : 0.f;
+      Bf[k] = 7.64e-6f * ((d0 + c0n) * s.cnorm[k]);
+    }
+    int j = 0;
+    float best = 0.f;
+#pragma unroll
+    for (int k = 1; k < KT; ++k)
+      if (dl[k] < best) { best = dl[k]; j = k; }
+    float epj = 0.f, Bj = 0.f;
+#pragma unroll
+    for (int k = 1; k < KT; ++k)
+      if (k == j) { epj = ep[k]; Bj = Bf[k]; }
+    const float D0 = F[0] + tail0;
+    const float E0 = 7.64e-6f * (F[0] + 2.f * (d0 * c0n)) + (c0n * 6.0e-8f) * (c0n * 6.0e-8f);
+    const float floor_ = 9.5e-10f * (D0 + __double2float_ru(s.hk[0]));
+    // deviation of D0 from d_0^2 beyond E0: roundings of x'_c (c0_c) and of the sums
+    const float epD = 6.0e-7f * D0 + 1.2e-7f * sqrtf(tail0) * s.fz[FZ_C0TN] +
+                      1.0e-12f * s.fz[FZ_C0TN] * s.fz[FZ_C0TN];
+    bool ok = (F[0] < 3.0e38f) && (j < K);
+    float second = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k != j) {
+        const float rhs = Bf[k] + Bj + floor_ + ep[k] + epj;
+        ok = ok && ((dl[k] - best) * 0.999999f > rhs * 1.00001f);
+        second = fminf(second, dl[k] - ep[k] - Bf[k]);
+      }
+    }
+    if (ok) {
+      if (bounds) {
+        const float slack = E0 + epD;
+        const float u2 = (D0 + best) + (slack + epj + Bj);
+        const float l2 = (D0 + second) - slack;
+        const float pad = 1.0e-6f * (D0 + fabsf(best) + fabsf(second));
+        a.ub[gr] = __fmul_ru(__fsqrt_ru(fmaxf(u2 + pad, 0.f)), 1.000001f);
+        a.lb[gr] = __fmul_rd(__fsqrt_rd(fmaxf(l2 - pad, 0.f)), 0.999999f);
+      }
+      return j;
+    }
+  }
+#ifdef KM_PROFILE
+  atomicAdd(&g_km_slow, 1ULL);
+#endif
   double delta[KT];
   delta[0] = 0.0;
 #pragma unroll
@@ -442,49 +539,81 @@ template <int KT>
 __device__ __forceinline__ int km_bounds_pass(const KmArgs& a, const KmSmem s, int64_t row_begin,
                                               int N, const int32_t* __restrict__ assign,
                                               const double* cdelta) {
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wq = t >> 5;
   const int K = a.K;
-  if (t < KT) s.dk[t] = t < K ? __double2float_ru(cdelta[t]) : 0.f;
-  __syncthreads();
-  if (t < KT) {
-    float m = 0.f;
-    for (int k = 0; k < K; ++k)
-      if (k != t) m = fmaxf(m, s.dk[k]);
-    bool bad = false;  // NaN drift (NaN centres) must keep every row active
-    for (int k = 0; k < K; ++k) bad |= !(s.dk[k] == s.dk[k]);
-    s.dexcl[t] = bad ? __int_as_float(0x7f800000) : m;
+  constexpr int NB = ACT_MAX / KM_THREADS;  // rows per thread: b * KM_THREADS + t
+  // all global loads first (one round trip): the centre drifts and the rows' state
+  float dk[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) dk[k] = k < K ? __double2float_ru(cdelta[k]) : 0.f;
+  int ai[NB];
+  float ub[NB], lb[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int i = b * KM_THREADS + t;
+    ai[b] = -1; ub[b] = 0.f; lb[b] = 0.f;
+    if (i < N) {
+      const int64_t gr = row_begin + i;
+      ai[b] = assign[gr];
+      ub[b] = a.ub[gr];
+      lb[b] = a.lb[gr];
+    }
   }
-  if (t == 0) *s.nact = 0;
-  __syncthreads();
-  __shared__ int wcnt[KM_THREADS / 32];
-  for (int i0 = 0; i0 < N; i0 += KM_THREADS) {
-    const int i = i0 + t;
+  // largest and second largest drift: the drift of "every other centre" is the largest one,
+  // or the second largest for the rows of the centre that moved most
+  float m1 = 0.f, m2 = 0.f;
+  int am = -1;
+  bool bad = false;  // NaN drift (NaN centres) must keep every row active
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    if (k < K) {
+      bad |= !(dk[k] == dk[k]);
+      if (dk[k] > m1) { m2 = m1; m1 = dk[k]; am = k; }
+      else if (dk[k] > m2) m2 = dk[k];
+    }
+  }
+  unsigned msk[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int i = b * KM_THREADS + t;
     bool active = false;
     if (i < N) {
       const int64_t gr = row_begin + i;
-      const int ai = assign[gr];
-      const bool okc = ai >= 0 && ai < K;
-      const float u2 = __fadd_ru(a.ub[gr], okc ? s.dk[ai] : 0.f);
-      const float l2 = __fsub_rd(a.lb[gr], okc ? s.dexcl[ai] : 0.f);
+      const bool okc = ai[b] >= 0 && ai[b] < K;
+      float own = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k == ai[b]) own = dk[k];
+      const float oth = bad ? __int_as_float(0x7f800000) : (ai[b] == am ? m2 : m1);
+      const float u2 = __fadd_ru(ub[b], okc ? own : 0.f);
+      const float l2 = __fsub_rd(lb[b], okc ? oth : 0.f);
       a.ub[gr] = u2;
       a.lb[gr] = l2;
       active = !(okc && u2 < l2);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, active);
-    if ((t & 31) == 0) wcnt[t >> 5] = __popc(m);
-    __syncthreads();
-    int before = *s.nact;
-    for (int q = 0; q < (t >> 5); ++q) before += wcnt[q];
-    if (active) s.act[before + __popc(m & ((1u << (t & 31)) - 1u))] = i;
-    __syncthreads();
-    if (t == 0) {
-      int tot = 0;
-      for (int q = 0; q < KM_THREADS / 32; ++q) tot += wcnt[q];
-      *s.nact += tot;
-    }
-    __syncthreads();
+    msk[b] = __ballot_sync(0xffffffffu, active);
   }
-  return *s.nact;
+  __shared__ int wcnt[NB][KM_THREADS / 32];
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) wcnt[b][wq] = __popc(msk[b]);
+  }
+  __syncthreads();
+  int run = 0;  // active rows before (b, warp) in row order
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    int before = run;
+#pragma unroll
+    for (int q = 0; q < KM_THREADS / 32; ++q) {
+      const int c = wcnt[b][q];
+      if (q < wq) before += c;
+      run += c;
+    }
+    if (msk[b] & (1u << lane))
+      s.act[before + __popc(msk[b] & ((1u << lane) - 1u))] = b * KM_THREADS + t;
+  }
+  __syncthreads();
+  return run;
 }
 
 // One pass over rows [row_begin, row_end).  mode 0: keep `assign`, omega = 1 (init means).
@@ -874,18 +1003,19 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
                                                 unsigned& wtile) {
   const int t = threadIdx.x, lane = t & 31, wq = t >> 5;
   const int K = a.K, Dr = a.Dr;
-  const unsigned row_bytes = (unsigned)a.copy16 * 16u;
   const char* Xb = reinterpret_cast<const char*>(a.X);
   char* wbuf = s.buf0 + (size_t)wq * 2 * R * a.srow;          // this warp's two R-row buffers
-  unsigned long long* wbar = s.bar + 2 + wq * 2;
   const int nsets = (na + R - 1) / R;                          // sets of R list entries
   constexpr int BR = 16;                                       // rows per decision batch
   constexpr int SPB = BR / R;
   __shared__ float stF[KM_THREADS / 32][BR * KT];
   __shared__ float stX[KM_THREADS / 32][BR * KM_NTAIL];
-  __shared__ signed char stA[KM_THREADS / 32][BR];             // assignment before the sweep
   const int my_n = nsets > wq ? (nsets - wq + 7) / 8 : 0;      // sets wq, wq + 8, ...
-  auto issue = [&](int set, unsigned gt) {
+  const int ntail = Dr - a.Dm;
+  const int st_r = ntail > 0 ? lane / ntail : 0, st_c = ntail > 0 ? lane - st_r * ntail : 0;
+  const unsigned row_bytes = (unsigned)a.copy16 * 16u;
+  unsigned long long* wbar = s.bar + 2 + wq * 2;
+  auto issue = [&](int set, unsigned gt) {  // bulk copies of the set's rows on the warp's mbarrier
     const int base = set * R;
     const int nv = min(R, na - base);
     char* dst = wbuf + (size_t)(gt & 1) * R * a.srow;
@@ -901,16 +1031,16 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
   long long last3__ = clock64();
 #endif
   if (my_n > 0) issue(wq, wtile);
+  int old_b = 0;  // lane q: assignment of the q-th row of the current batch before the sweep
   for (int i = 0; i < my_n; ++i) {
     const int set = wq + 8 * i;
-    const unsigned gt = wtile + (unsigned)i;
+    const int sb = i % SPB;  // set within the batch
     __syncwarp();  // every lane is done reading the buffer the next copy overwrites
+    const unsigned gt = wtile + (unsigned)i;
     if (i + 1 < my_n) issue(set + 8, gt + 1);
-    // the row's current assignment travels with it (loaded while the copy is in flight)
-    int old_a = 0;
-    {
-      const int pos_l = (wq + 8 * i) * R + lane;
-      if (lane < R && pos_l < na) old_a = assign[row_begin + (s.act[pos_l] & ACT_ROW)];
+    if (sb == 0) {
+      const int pos = (wq + 8 * (i + lane / R)) * R + lane % R;
+      if (lane < BR && pos < na) old_b = assign[row_begin + (s.act[pos] & ACT_ROW)];
     }
     KM_TICK3(0);
     mbar_wait(wbar + (gt & 1), (gt >> 1) & 1);
@@ -918,9 +1048,11 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
     const char* xw = wbuf + (size_t)(gt & 1) * R * a.srow;
     const float tot = km_screen_partial<KT, R>(a, s, xw);
     KM_TICK3(2);
-    const int sb = i % SPB;  // set within the batch
-    km_screen_stage<KT, R>(a, xw, tot, stF[wq], stX[wq], sb * R);
-    if (lane < R) stA[wq][sb * R + lane] = (signed char)old_a;
+    if (lane < R * KT) stF[wq][sb * R * KT + lane] = tot;
+    if (lane < R * ntail)
+      stX[wq][(sb * R + st_r) * KM_NTAIL + st_c] =
+          reinterpret_cast<const float*>(xw + (size_t)st_r * a.srow)[a.Dm + st_c];
+    KM_TICK3(3);
     if (sb == SPB - 1 || i == my_n - 1) {
       // decide the batch: lane q takes the q-th staged row
       __syncwarp();
@@ -928,7 +1060,6 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
       const int pos = (wq + 8 * (i0 + lane / R)) * R + lane % R;   // list position of the row
       if (lane < (sb + 1) * R && pos < na) {
         const int64_t gr = row_begin + (s.act[pos] & ACT_ROW);
-        const int old = stA[wq][lane];
         float F[KT], xt[KM_NTAIL];
 #pragma unroll
         for (int k = 0; k < KT; ++k) F[k] = stF[wq][lane * KT + k];
@@ -938,15 +1069,18 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
         int e = s.act[pos] & ACT_ROW;
         if (j < 0) {
           e |= ACT_AMB;
-        } else if (j != old) {
-          e |= ACT_CHG | (j << ACT_NEW_SHIFT) | ((old & 15) << ACT_OLD_SHIFT);
+        } else if (j != old_b) {
+          e |= ACT_CHG | (j << ACT_NEW_SHIFT) | ((old_b & 15) << ACT_OLD_SHIFT);
           assign[gr] = j;
         }
         s.act[pos] = e;
       }
       __syncwarp();
+#ifdef KM_PROFILE
+      prof3__[6] += 1;
+#endif
     }
-    KM_TICK3(3);
+    KM_TICK3(5);
   }
 #ifdef KM_PROFILE
   prof3__[7] += my_n;
@@ -1146,12 +1280,43 @@ __device__ __forceinline__ void prepare_screen(const KmArgs& a, const KmSmem s) 
       if (wq >= 1) s.hk[wq] = wq < a.K ? -e : -1.0e300;  // delta = dot - hk: dummies far away
     }
   }
+  // fp32 constants of the fast decision path, over the nt columns outside the screening loop
+  // (tail column c is column Dm + c, stored or virtual):
+  //   gt[k][c] = 2(c0_c - ck_c), c0t[c] = c0_c, ek[k] = ||c0 - ck||^2 over ALL columns,
+  //   ak[k] >= sum_c |gt[k][c]| |c0_c|, c0tn >= ||c0 tail||
+  if (t < KT) {
+    const int nt = a.D - main_d;
+    double ek = 0.0, ak = 0.0;
+    for (int c = 0; c < KM_NT; ++c) {
+      double g = 0.0;
+      if (c < nt && t < a.K) {
+        const double c0 = s.cen[main_d + c], ck = s.cen[(size_t)t * a.Dc + main_d + c];
+        g = 2.0 * (c0 - ck);
+        ek = fma(c0 - ck, c0 - ck, ek);
+        ak += fabs(g) * fabs(c0);
+      }
+      s.fz[FZ_GT + t * KM_NT + c] = (float)g;
+    }
+    s.fz[FZ_AK + t] = __double2float_ru(ak) * 1.001f;
+    s.red[KMAX + t] = ek;  // tail share of e_k; the main share is -hk[k], added below
+  }
+  if (t == KT) {
+    const int nt = a.D - main_d;
+    double n2 = 0.0;
+    for (int c = 0; c < KM_NT; ++c) {
+      const double c0 = c < nt ? s.cen[main_d + c] : 0.0;
+      s.fz[FZ_C0T + c] = (float)c0;
+      n2 = fma(c0, c0, n2);
+    }
+    s.fz[FZ_C0TN] = __double2float_ru(sqrt(n2)) * 1.001f;
+  }
   __syncthreads();
   if (t == 0) {
     double m = 0.0;
     for (int k = 0; k < a.K; ++k) m = fmax(m, s.red[k]);   // NaN centres: fmax skips them,
     s.hk[0] = m;                                            // the row test catches NaN deltas
   }
+  if (t >= 1 && t < KT) s.fz[FZ_EK + t] = (float)(s.red[KMAX + t] - s.hk[t]);
   __syncthreads();
 }
 
@@ -1439,6 +1604,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   int it = g.iters[grp];
   int status = SPALIGN_KM_ITER_CAP;
   unsigned tile_base = 0, wtile = 0;
+  bool first = true;
   double acc[KT][NS2][2];
 #ifdef KM_PROFILE
   long long prof2__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1448,7 +1614,9 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
     zero_acc<KT, NS2>(acc);
     if (t == 0) *s.changed = 0;
     if (t < KMAX * 4) xs[t] = 0.0;
-    prepare_screen<KT>(g.a, s);  // ends with a block barrier
+    if (first) prepare_screen<KT>(g.a, s);  // later iterations: done by the centre update
+    first = false;
+    __syncthreads();
     KM_TICK2(0);
     for (int64_t rb = r0; rb < r1; rb += ACT_MAX) {
       const int n = (int)min((int64_t)ACT_MAX, r1 - rb);
@@ -1494,42 +1662,106 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       s.extra[t * 4 + 2] = dp;
     }
     __syncthreads();
-    double d2[KT];
+    // every thread owns its columns of all K centres: new centres, their drift, and -- in the
+    // same pass -- everything the next iteration's screening needs (what prepare_screen
+    // computes from scratch): cen32 = c_0 | g_k, e_k = ||c_0 - c_k||^2, ||c_k||^2
+    double q[KT][3];   // per cluster: drift^2, e_k over the fp32 columns, ||c_k||^2 (stored)
+    double c2m = 0.0;  // ||c_0||^2 over the fp32 columns
 #pragma unroll
-    for (int k = 0; k < KT; ++k) d2[k] = 0.0;
+    for (int k = 0; k < KT; ++k) q[k][0] = q[k][1] = q[k][2] = 0.0;
 #pragma unroll
     for (int sl = 0; sl < NS2; ++sl) {
-      const int c0 = 2 * (sl * KM_THREADS + t);
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        if (k < K) {
-          const double ws = s.extra[k * 4 + 0];
+      for (int j = 0; j < 2; ++j) {
+        const int c = 2 * (sl * KM_THREADS + t) + j;
+        if (c < Dr) {
+          const bool mainc = c < g.a.Dm;
+          double cn0 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (c0 + j < Dr) {
-              const size_t idx = (size_t)k * (D + 2) + c0 + j;
+          for (int k = 0; k < KT; ++k) {
+            if (k < K) {
+              const size_t idx = (size_t)k * (D + 2) + c;
               const double v = tt[idx] + acc[k][sl][j];
               tt[idx] = v;
-              const double nv = v / ws;
-              const double df = nv - s.cen[(size_t)k * Dc + c0 + j];
-              d2[k] = fma(df, df, d2[k]);
-              s.cen[(size_t)k * Dc + c0 + j] = nv;
+              const double nv = v / s.extra[k * 4 + 0];
+              const double df = nv - s.cen[(size_t)k * Dc + c];
+              q[k][0] = fma(df, df, q[k][0]);
+              s.cen[(size_t)k * Dc + c] = nv;
+              q[k][2] = fma(nv, nv, q[k][2]);
+              if (k == 0) {
+                cn0 = nv;
+                if (mainc) c2m = fma(nv, nv, c2m);
+                s.cen32[c] = mainc ? (float)nv : 0.f;
+              } else {
+                const double dd = cn0 - nv;
+                if (mainc) q[k][1] = fma(dd, dd, q[k][1]);
+                s.cen32[(size_t)k * Dc + c] = mainc ? (float)(2.0 * dd) : 0.f;
+              }
             }
           }
         }
       }
     }
+    // block sums in a fixed order: lanes (xor tree), then warps
+    __shared__ double redq[KM_THREADS / 32][3 * KMAX + 1];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], o);
-      if ((t & 31) == 0) s.red[(size_t)(t >> 5) * KMAX + k] = d2[k];
+      for (int u = 0; u < 3; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q[k][u] += __shfl_xor_sync(0xffffffffu, q[k][u], o);
+        if ((t & 31) == 0) redq[t >> 5][k * 3 + u] = q[k][u];
+      }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c2m += __shfl_xor_sync(0xffffffffu, c2m, o);
+    if ((t & 31) == 0) redq[t >> 5][3 * KMAX] = c2m;
     __syncthreads();
-    if (t < K) {
-      double sum = s.extra[t * 4 + 2];
-      for (int q = 0; q < KM_THREADS / 32; ++q) sum += s.red[(size_t)q * KMAX + t];
-      cd[t] = sqrt(sum) * (1.0 + 1e-12);
+    if (t < KT) {
+      const bool in = t < K;
+      double d2s = 0.0, es = 0.0, c2s = 0.0, c2ms = 0.0;
+      for (int w8 = 0; w8 < KM_THREADS / 32; ++w8) {
+        d2s += redq[w8][t * 3 + 0];
+        es += redq[w8][t * 3 + 1];
+        c2s += redq[w8][t * 3 + 2];
+        c2ms += redq[w8][3 * KMAX];
+      }
+      if (in) {
+        cd[t] = sqrt(d2s + s.extra[t * 4 + 2]) * (1.0 + 1e-12);
+        if (g.a.pos_mode) {
+          const double px = s.cen[(size_t)t * Dc + Dr], py = s.cen[(size_t)t * Dc + Dr + 1];
+          c2s = fma(px, px, fma(py, py, c2s));
+        }
+      }
+      if (t == 0) s.cnorm[0] = (float)sqrt(c2ms) * 1.0001f;
+      else s.cnorm[t] = in ? (float)sqrt(4.0 * es) * 1.0001f : 0.f;
+      s.red[t] = in ? c2s : 0.0;
+      if (t >= 1) s.hk[t] = in ? -es : -1.0e300;
+      // fp32 constants of the fast decision path (see prepare_screen)
+      const int nt = D - g.a.Dm;
+      double ek = 0.0, ak = 0.0;
+      for (int c = 0; c < KM_NT; ++c) {
+        double gg = 0.0;
+        if (c < nt && in) {
+          const double c0 = s.cen[g.a.Dm + c], ck = s.cen[(size_t)t * Dc + g.a.Dm + c];
+          gg = 2.0 * (c0 - ck);
+          ek = fma(c0 - ck, c0 - ck, ek);
+          ak += fabs(gg) * fabs(c0);
+        }
+        s.fz[FZ_GT + t * KM_NT + c] = (float)gg;
+      }
+      s.fz[FZ_AK + t] = __double2float_ru(ak) * 1.001f;
+      if (t >= 1) s.fz[FZ_EK + t] = (float)(ek + (in ? es : 1.0e300));
+    }
+    if (t == KT) {
+      const int nt = D - g.a.Dm;
+      double n2 = 0.0;
+      for (int c = 0; c < KM_NT; ++c) {
+        const double c0 = c < nt ? s.cen[g.a.Dm + c] : 0.0;
+        s.fz[FZ_C0T + c] = (float)c0;
+        n2 = fma(c0, c0, n2);
+      }
+      s.fz[FZ_C0TN] = __double2float_ru(sqrt(n2)) * 1.001f;
     }
     bool empty = false;
     for (int k = 0; k < K; ++k) empty |= (s.extra[k * 4 + 1] == 0.0);
@@ -1538,6 +1770,11 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       break;
     }
     __syncthreads();
+    if (t == 0) {  // magnitude scale of the float64 floor (read after the next block barriers)
+      double m = 0.0;
+      for (int k = 0; k < K; ++k) m = fmax(m, s.red[k]);
+      s.hk[0] = m;
+    }
     KM_TICK2(3);
   }
   __syncthreads();
@@ -1935,10 +2172,16 @@ extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
       fprintf(stderr, "[km_profile] finish kernel: iterations=%llu  cycles/iteration (thread 0): prepare %.0f | bounds %.0f | sweep %.0f | update %.0f\n",
               p[4], (double)p[0] / p[4], (double)p[1] / p[4], (double)p[2] / p[4], (double)p[3] / p[4]);
     cudaMemcpyToSymbol(g_km_prof2, z, sizeof(z));
+    {
+      unsigned long long slow = 0, zero = 0;
+      cudaMemcpyFromSymbol(&slow, g_km_slow, sizeof(slow));
+      cudaMemcpyToSymbol(g_km_slow, &zero, sizeof(zero));
+      fprintf(stderr, "[km_profile] rows that took the float64 decision path: %llu\n", slow);
+    }
     cudaMemcpyFromSymbol(p, g_km_prof3, sizeof(p));
     if (p[7])
-      fprintf(stderr, "[km_profile] sparse sweep, warp 0: sets=%llu  cycles/set: issue %.0f | wait %.0f | partial %.0f | stage+decide %.0f ; exact+compaction per set %.0f\n",
-              p[7], (double)p[0] / p[7], (double)p[1] / p[7], (double)p[2] / p[7], (double)p[3] / p[7], (double)p[4] / p[7]);
+      fprintf(stderr, "[km_profile] sparse sweep, warp 0: sets=%llu  cycles/set: issue %.0f | wait %.0f | partial %.0f | stage %.0f ; exact+compaction per set %.0f ; decide calls %llu, cycles each %.0f\n",
+              p[7], (double)p[0] / p[7], (double)p[1] / p[7], (double)p[2] / p[7], (double)p[3] / p[7], (double)p[4] / p[7], p[6], (double)p[5] / (p[6] ? p[6] : 1));
     cudaMemcpyToSymbol(g_km_prof3, z, sizeof(z));
     {
       Plan plan;

@@ -629,16 +629,26 @@ _OUT_CODES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64
 
 def paint(labels: torch.Tensor, sp_off: torch.Tensor, table: torch.Tensor,
           out_dtype: Optional[torch.dtype] = torch.uint8, want_mask: bool = True,
-          road_value: int = 0):
+          road_value: int = 0, out=None):
     """K4: cluster_map[p] = table[sp_off[img] + label[p]], road_mask = (cluster_map == road_value).
-    Returns (cluster_map or None, road_mask uint8 or None)."""
+    Returns (cluster_map or None, road_mask uint8 or None).  ``out`` = (cluster_map, road_mask)
+    contiguous [n, H, W] tensors to write into (e.g. slices of a larger batch)."""
     _require_cuda(labels, sp_off, table)
     labels = labels.contiguous()
     n, H, W = labels.shape
     dev = labels.device
     table = table.to(torch.int32).contiguous()
-    cmap = torch.empty((n, H, W), dtype=out_dtype, device=dev) if out_dtype is not None else None
-    mask = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    if out is not None:
+        cmap, mask = out
+        for o in (cmap, mask):
+            if o is not None and (not o.is_contiguous() or tuple(o.shape) != (n, H, W)):
+                raise ValueError('paint: out tensors must be contiguous [n, H, W]')
+        if mask is not None and mask.dtype != torch.uint8:
+            raise ValueError('paint: road mask must be uint8')
+        out_dtype = cmap.dtype if cmap is not None else None
+    else:
+        cmap = torch.empty((n, H, W), dtype=out_dtype, device=dev) if out_dtype is not None else None
+        mask = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_mask else None
     check(_lib.load().spalign_paint(
         _ptr(labels), _label_code(labels), n, H, W, _ptr(sp_off), _ptr(table), _ptr(cmap),
         _OUT_CODES[out_dtype] if out_dtype is not None else _lib.U8, _ptr(mask), road_value,

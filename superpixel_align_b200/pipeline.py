@@ -54,7 +54,8 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
               fw: int, k: int = 4, prior=(0.75, 0.5, 0.1, 0.1), append_pos: bool = True,
               images_per_group: int = 1, n_iter: int = 1000,
               nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8,
-              timers: Optional[dict] = None, kmeans_impl: str = 'chunks') -> PipelineOutput:
+              timers: Optional[dict] = None, kmeans_impl: str = 'chunks',
+              out=None) -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
     1 = per-image clustering).  Groups of more than 4096 rows use the host-driven multi-CTA
@@ -122,10 +123,82 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
                               group_off_host, n_iter=n_iter).run()
         mark('kmeans', False)
     mark('paint', True)
-    cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype)
+    cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype, out=out)
     mark('paint', False)
     return PipelineOutput(cmap, mask, res.assign, feats, weights, res.iters, res.status, m, ov,
                           group_off_host, m_exp)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev, n):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _SIDE_STREAMS[key]
+
+
+@dataclass
+class OverlappedOutput:
+    cluster_map: torch.Tensor   # uint8 [n, H, W]
+    road_mask: torch.Tensor     # uint8 [n, H, W]
+    parts: list                 # PipelineOutput per sub-batch, in image order
+
+    @property
+    def iters(self):
+        return torch.cat([p.iters for p in self.parts])
+
+    @property
+    def status(self):
+        return torch.cat([p.status for p in self.parts])
+
+    @property
+    def assign(self):
+        return torch.cat([p.assign for p in self.parts])
+
+
+def run_batch_overlapped(labels: torch.Tensor, feat_cellmajor: torch.Tensor,
+                         n_sp: Sequence[int], fh: int, fw: int, sub_batch: int = 60,
+                         n_streams: int = 2, out_dtype=torch.uint8, timers: Optional[list] = None,
+                         **kw) -> OverlappedOutput:
+    """``run_batch`` over sub-batches of ``sub_batch`` images that alternate between
+    ``n_streams`` CUDA streams.  The stages of one sub-batch have very different appetites --
+    K2/K4 stream HBM at full bandwidth, the k-means tail is a latency-bound handful of CTAs
+    waiting for its slowest images -- so running two sub-batches side by side lets the pooling
+    of one fill the SMs and the memory system that the k-means tail of the other leaves idle.
+    Same results as one ``run_batch`` call (the seeded init consumes ``np.random`` in image
+    order either way); the outputs land in one [n, H, W] pair.  The calling stream waits for
+    all side streams before this returns (no host synchronisation)."""
+    n, H, W = labels.shape
+    dev = labels.device
+    n_sp = np.asarray(n_sp, dtype=np.int64)
+    cmap = torch.empty((n, H, W), dtype=out_dtype, device=dev)
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+    main = torch.cuda.current_stream()
+    streams = _side_streams(dev, n_streams)
+    start = torch.cuda.Event()
+    start.record(main)
+    parts = []
+    for j, i0 in enumerate(range(0, n, sub_batch)):
+        i1 = min(n, i0 + sub_batch)
+        st = streams[j % n_streams]
+        with torch.cuda.stream(st):
+            if j < n_streams:
+                st.wait_event(start)
+            tm = {} if timers is not None else None
+            parts.append(run_batch(labels[i0:i1], feat_cellmajor[i0:i1], n_sp[i0:i1], fh, fw,
+                                   timers=tm, out=(cmap[i0:i1], mask[i0:i1]), **kw))
+            if timers is not None:
+                timers.append(tm)
+    for st in streams:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
+    for t in (cmap, mask):
+        for st in streams:
+            t.record_stream(st)
+    return OverlappedOutput(cmap, mask, parts)
 
 
 class HostPipeline:
