@@ -196,16 +196,13 @@ int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, 
  * an upper bound on the distance to its centre and a lower bound on the distance to any other
  * centre; every update records how far each centre moved; a mode-2 sweep shifts the bounds by
  * that drift and only gathers, screens and re-bounds the rows whose bounds no longer prove that
- * the assignment is unchanged (fp32 rows, chunks of <= 1024 rows).  Results are identical.
- * xflag (optional, device int32[1], zero before the mode-0 call): the mode-0 sweep sets it when
- * X holds a denormal / inf / NaN; when it stays 0 the mode-1 sweeps convert fp32 -> fp64 on the
- * integer pipe instead of the (slow) FP64 pipe -- same values, exact. */
+ * the assignment is unchanged (fp32 rows, chunks of <= 1024 rows).  Results are identical. */
 int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
                            int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
                            const int64_t* chunks, int n_chunks, const int32_t* group_chunk_off,
                            int mode, int n_iter, int32_t* assign, double* partials,
                            double* totals, double* centers, int32_t* iters, int32_t* status,
-                           int32_t* counters, int32_t* xflag, float* ub, float* lb,
+                           int32_t* counters, float* ub, float* lb,
                            double* cdelta, spalign_stream_t stream);
 /* Runs every group that is still SPALIGN_KM_RUNNING to its stop condition in ONE launch: one
  * persistent CTA per group repeats mode-2 iterations (bounds pass, gather + screen the rows the

@@ -50,6 +50,7 @@ __device__ unsigned long long g_km_stats[2];
 #ifdef KM_PROFILE
 __device__ unsigned long long g_km_prof[8];
 __device__ unsigned long long g_km_prof2[8];
+__device__ unsigned long long g_km_prof4[16];
 __device__ unsigned long long g_km_prof3[8];
 __device__ unsigned long long g_km_slow;
 #define KM_TICK3(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof3__[i] += now__ - last3__; last3__ = now__; } } while (0)
@@ -236,21 +237,6 @@ __device__ __forceinline__ void issue_tile(const KmArgs& a, char* buf, unsigned 
   for (int r = lane; r < nvalid; r += 32)
     bulk_g2s(buf + (size_t)r * a.srow, src + ((size_t)(row0 + r) * a.ldx) * sizeof(XT), row_bytes,
              bar);
-}
-
-// fp32 -> fp64 on the integer pipe.  B200's FP64 pipe runs at ~1/16 of the FP32 rate and phase
-// 2 is bound by it; F2F.F64.F32 runs on that pipe too.  Exact for zeros and normal numbers;
-// the init sweep (mode 0) checks every element once and the fast path is only taken when the
-// matrix holds no denormal / inf / NaN (xflag == 0).
-__device__ __forceinline__ double f2d_normal(float x) {
-  const unsigned b = __float_as_uint(x);
-  const unsigned em = b & 0x7fffffffu;
-  const unsigned hi = (b & 0x80000000u) | ((em >> 3) + (em ? 0x38000000u : 0u));
-  return __hiloint2double((int)hi, (int)(em << 29));
-}
-__device__ __forceinline__ bool f32_special(float x) {  // denormal, inf or NaN
-  const unsigned em = __float_as_uint(x) & 0x7fffffffu;
-  return em != 0u && (em - 0x00800000u) >= 0x7f000000u;
 }
 
 // virtual position columns of global row n (direct_clustering.py:300-303): (x, y) cell index
@@ -623,7 +609,7 @@ template <typename XT, int KT, int NS2, int R>
 __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_t row_begin,
                                          int64_t row_end, int mode, int32_t* __restrict__ assign,
                                          double (&acc)[KT][NS2][2], unsigned& tile_base,
-                                         int32_t* xflag = nullptr, int nrows_in = -1) {
+                                         int nrows_in = -1) {
   constexpr int VE = 16 / (int)sizeof(XT);
   constexpr bool kF32 = sizeof(XT) == 4;
   const int t = threadIdx.x;
@@ -655,9 +641,6 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
   long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long last__ = clock64();
 #endif
-  // fast conversion only for fp32 rows that the init sweep found free of special values
-  const bool fastcvt = kF32 && mode != 0 && xflag != nullptr && *xflag == 0;
-  bool saw_special = false;
   const int lane_ = t & 31, wq_ = t >> 5;
   unsigned short* my_order = s.order + wq_ * 32;      // per-warp copy of the tile's row grouping
   double* my_om = s.om + wq_ * 32;
@@ -932,14 +915,8 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
               double x0, x1;
               if (kF32) {
                 const float2 v = *reinterpret_cast<const float2*>(xr + c0);
-                if (fastcvt) {
-                  x0 = f2d_normal(v.x);
-                  x1 = f2d_normal(v.y);
-                } else {
-                  x0 = (double)v.x;
-                  x1 = (double)v.y;
-                  if (mode == 0) saw_special |= f32_special(v.x) | f32_special(v.y);
-                }
+                x0 = (double)v.x;
+                x1 = (double)v.y;
               } else {
                 const double2 v = *reinterpret_cast<const double2*>(xr + c0);
                 x0 = v.x;
@@ -958,7 +935,6 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             for (int i = startk[k]; i < i1; ++i) {
               const XT* xr =
                   reinterpret_cast<const XT*>(tile + (size_t)(my_order[i] & 0xff) * a.srow);
-              if (kF32 && mode == 0) saw_special |= f32_special((float)xr[c0]);
               acc[k][sl][0] = fma(my_om[i], (double)xr[c0], acc[k][sl][0]);
             }
           }
@@ -967,12 +943,13 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     }
     KM_TICK(4);
   }
-  if (kF32 && mode == 0 && xflag != nullptr && saw_special) atomicOr(xflag, 1);
   __syncthreads();
 #ifdef KM_PROFILE
-  if (threadIdx.x == 0 && compact) {  // compacted mode-2 sweeps only
-    for (int i = 0; i < 6; ++i) atomicAdd(&g_km_prof[i], (unsigned long long)prof__[i]);
-    atomicAdd(&g_km_prof[6], (unsigned long long)ntiles);
+  if (threadIdx.x == 0) {  // [0]: compacted (mode 3) tiles, [1]: mode 0, [2]: mode 1
+    unsigned long long* dst = compact ? g_km_prof : (mode == 0 ? g_km_prof4 : g_km_prof4 + 8);
+    for (int i = 0; i < 6; ++i) atomicAdd(&dst[i], (unsigned long long)prof__[i]);
+    atomicAdd(&dst[6], (unsigned long long)ntiles);
+    atomicAdd(&dst[7], 1ULL);
   }
 #endif
 #undef KM_ROW
@@ -1192,7 +1169,7 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
   }
 #endif
   km_sweep<float, KT, NS2, R>(a, s, row_begin, row_begin + ACT_MAX, 3, assign, acc, tile_base,
-                              nullptr, nchg);
+                              nchg);
 }
 
 template <int KT, int NS2>
@@ -1400,7 +1377,6 @@ struct SweepArgs {
   int32_t* iters;
   int32_t* status_rw;
   int n_iter;
-  int32_t* xflag;         // [1] set by the mode-0 sweep when X holds denormal/inf/NaN; may be NULL
   double* cdelta;         // [G][K] centre drift of the last update (Hamerly bounds); may be NULL
 };
 
@@ -1493,10 +1469,10 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
         unsigned wtile = 0;
         km_sweep_sparse<KT, NS2, R>(g.a, s, rb, nrows_in, g.assign, acc, tile_base, wtile);
       } else {
-        km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
+        km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base);
       }
     } else {
-      km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base, g.xflag);
+      km_sweep<XT, KT, NS2, R>(g.a, s, rb, re, g.mode, g.assign, acc, tile_base);
     }
   } else if (t < K) {
     s.extra[t * 4 + 0] = s.extra[t * 4 + 1] = s.extra[t * 4 + 2] = s.extra[t * 4 + 3] = 0.0;
@@ -2056,7 +2032,7 @@ extern "C" int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
   g.gco = nullptr; g.counters = nullptr; g.totals = nullptr; g.centers_rw = nullptr;
-  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.xflag = nullptr; g.cdelta = nullptr;
+  g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.cdelta = nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_sweep");
 }
@@ -2067,7 +2043,7 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
                                       int n_chunks, const int32_t* group_chunk_off, int mode,
                                       int n_iter, int32_t* assign, double* partials,
                                       double* totals, double* centers, int32_t* iters,
-                                      int32_t* status, int32_t* counters, int32_t* xflag,
+                                      int32_t* status, int32_t* counters,
                                       float* ub, float* lb, double* cdelta,
                                       spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -2087,7 +2063,7 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
   g.chunks = chunks; g.centers = centers; g.mode = mode; g.assign = assign; g.status = status;
   g.partials = partials;
   g.gco = group_chunk_off; g.counters = counters; g.totals = totals; g.centers_rw = centers;
-  g.iters = iters; g.status_rw = status; g.n_iter = n_iter; g.xflag = xflag;
+  g.iters = iters; g.status_rw = status; g.n_iter = n_iter;
   g.cdelta = (ub && lb) ? cdelta : nullptr;
   g.a.ub = cdelta ? ub : nullptr; g.a.lb = cdelta ? lb : nullptr;
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
@@ -2167,6 +2143,17 @@ extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
     }
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_km_prof, z, sizeof(z));
+    {
+      unsigned long long p4[16], z4[16] = {0};
+      cudaMemcpyFromSymbol(p4, g_km_prof4, sizeof(p4));
+      for (int m = 0; m < 2; ++m) {
+        const unsigned long long* q = p4 + 8 * m;
+        if (q[6])
+          fprintf(stderr, "[km_profile] full sweep mode %d: CTAs=%llu tiles=%llu  cycles/tile (thread 0): barrierA %.0f | issue %.0f | tile wait %.0f | phase1+decide %.0f | grouping %.0f | phase2 %.0f\n",
+                  m, q[7], q[6], (double)q[0] / q[6], (double)q[5] / q[6], (double)q[1] / q[6], (double)q[2] / q[6], (double)q[3] / q[6], (double)q[4] / q[6]);
+      }
+      cudaMemcpyToSymbol(g_km_prof4, z4, sizeof(z4));
+    }
     cudaMemcpyFromSymbol(p, g_km_prof2, sizeof(p));
     if (p[4])
       fprintf(stderr, "[km_profile] finish kernel: iterations=%llu  cycles/iteration (thread 0): prepare %.0f | bounds %.0f | sweep %.0f | update %.0f\n",

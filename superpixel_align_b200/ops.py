@@ -427,7 +427,6 @@ class KMeansLarge:
         self.iters = torch.zeros(self.G, dtype=torch.int32, device=dev)
         self.status = torch.full((self.G,), _lib.KM_RUNNING, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(self.G, dtype=torch.int32, device=dev)
-        self.xflag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ub = self.lb = self.cdelta = None
         if bounds and incremental and fused and self.code == _lib.F32:
             self.ub = torch.empty(self.N, dtype=torch.float32, device=dev)
@@ -508,7 +507,7 @@ class KMeansLarge:
                 self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
                 self.n_chunks, _ptr(self.gco), mode, self.n_iter, _ptr(self.assign),
                 _ptr(self.partials), _ptr(self.totals), _ptr(self.centers), _ptr(self.iters),
-                _ptr(self.status), _ptr(self.counters), _ptr(self.xflag), _ptr(self.ub),
+                _ptr(self.status), _ptr(self.counters), _ptr(self.ub),
                 _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_iterate')
             _count('kmeans_sweep')
             return

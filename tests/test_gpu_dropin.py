@@ -184,6 +184,25 @@ def test_host_pipeline_streams_batches_and_matches_device_path():
         assert torch.equal(ref.road_mask.cpu(), got[i][1])
 
 
+def test_run_batch_overlapped_on_side_streams_equals_one_batch():
+    from superpixel_align_b200 import pipeline
+    d = torch.device('cuda', 0)
+    H, W, fh, fw, C = 128, 256, 16, 32, 32
+    n = 7
+    labs = torch.from_numpy(np.stack([synth.voronoi_labels(H, W, 6, 10, image_index=i) for i in range(n)])).to(d)
+    feats = torch.from_numpy(np.ascontiguousarray(np.stack(
+        [synth.smooth_features(C, fh, fw, seed=i).reshape(C, -1).T for i in range(n)]))).to(d)
+    np.random.seed(3)
+    ref = pipeline.run_batch(labs, feats, [60] * n, fh, fw, k=4)
+    for sb, ns in ((3, 2), (2, 3), (7, 2)):
+        np.random.seed(3)
+        out = pipeline.run_batch_overlapped(labs, feats, [60] * n, fh, fw, sub_batch=sb, n_streams=ns, k=4)
+        torch.cuda.synchronize()
+        assert torch.equal(out.cluster_map, ref.cluster_map) and torch.equal(out.road_mask, ref.road_mask)
+        assert torch.equal(out.iters, ref.iters) and torch.equal(out.assign, ref.assign)
+        assert len(out.parts) == -(-n // sb)
+
+
 def test_results_scores_and_artefacts(tmp_path):
     from superpixel_align_b200 import results
     rs = np.random.RandomState(1)

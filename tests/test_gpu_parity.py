@@ -352,6 +352,11 @@ def test_kmeans_direct_virtual_position_columns(ops):
     km = ops.KMeansLarge(cell, torch.from_numpy(prior).to(dev()), torch.from_numpy(init).to(dev()),
                          4, [0, n * h * w_], pos_grid=(h, w_), chunks_per_group=4).run()
     assert np.array_equal(km.assign.cpu().numpy(), np.asarray(want).astype(np.int32))
+    # persistent finish kernel with the virtual columns
+    kt = ops.KMeansLarge(cell, torch.from_numpy(prior).to(dev()), torch.from_numpy(init).to(dev()),
+                         4, [0, n * h * w_], pos_grid=(h, w_))
+    assert kt.tail
+    assert np.array_equal(kt.run().assign.cpu().numpy(), np.asarray(want).astype(np.int32))
     # and the materialised matrix through the plain path gives the same answer
     res2 = ops.kmeans_groups(torch.from_numpy(X.astype(np.float32)).to(dev()),
                              torch.from_numpy(prior).to(dev()), torch.from_numpy(init).to(dev()), 4, goff)
@@ -497,6 +502,55 @@ def test_kmeans_fused_iterate_equals_three_kernel_path(ops):
     for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
         want = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64), verbose=False)
         assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
+
+
+@pytest.mark.parametrize('sizes,tail_rows', [([900, 1000, 64, 1700, 1], 2048), ([2500, 3100, 1025], 4096)])
+def test_kmeans_finish_kernel_equals_per_iteration_launches(ops, sizes, tail_rows, monkeypatch):
+    # one persistent CTA per group (spalign_kmeans_finish; groups above 1024 rows loop over
+    # sub-chunks) against one launch per iteration, and both against the oracle
+    monkeypatch.setattr(ops.KMeansLarge, 'TAIL_ROWS', tail_rows)
+    rs = np.random.RandomState(33)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = _blobs(rs, off[-1], 514, 4)
+    X[:, -2] = rs.uniform(0, 1023, len(X)); X[:, -1] = rs.uniform(0, 2047, len(X))
+    w = rs.uniform(0, 1, len(X))
+    init = np.concatenate([so.kmeans_init(4, w[a:b], rng=rs) if b - a > 1 else np.zeros(b - a)
+                           for a, b in zip(off[:-1], off[1:])]).astype(np.int32)
+    args = (torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()), torch.from_numpy(init).to(dev()), 4, off)
+    km = ops.KMeansLarge(*args)
+    assert km.tail
+    l0 = ops.LAUNCHES
+    a = km.run()
+    assert ops.LAUNCHES - l0 == 3          # init sums, first full iteration, finish kernel
+    b = ops.KMeansLarge(*args, tail=False).run()
+    assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
+    assert torch.equal(a.status, b.status)
+    for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        if a.status[g].item() == 0:        # centres of converged groups: same up to summation order
+            torch.testing.assert_close(a.centers[g], b.centers[g], rtol=1e-10, atol=1e-10)
+        want, info = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64),
+                               return_info=True, verbose=False)
+        assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
+        assert a.iters[g].item() == info['iters'] and a.status[g].item() == info['status']
+
+
+def test_kmeans_finish_kernel_iteration_cap(ops):
+    rs = np.random.RandomState(5)
+    X = _blobs(rs, 1500, 66, 4, spread=0.4)   # heavily overlapping blobs: many iterations
+    w = rs.uniform(0, 1, 1500)
+    init = so.kmeans_init(4, w, rng=rs).astype(np.int32)
+    full = ops.KMeansLarge(torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()),
+                           torch.from_numpy(init).to(dev()), 4, [0, 1500]).run()
+    n_full = full.iters[0].item()
+    assert n_full >= 4
+    for cap in (1, 2, n_full - 1):
+        km = ops.KMeansLarge(torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()),
+                             torch.from_numpy(init).to(dev()), 4, [0, 1500], n_iter=cap).run()
+        want, info = so.kmeans(4, X.astype(np.float64), w, n_iter=cap, init_assign=init.astype(np.float64),
+                               return_info=True, verbose=False)
+        assert km.iters[0].item() == cap == info['iters']
+        assert km.status[0].item() == info['status']
+        assert np.array_equal(km.assign.cpu().numpy(), np.asarray(want).astype(np.int32))
 
 
 # ------------------------------------------------------------------- f2 bilinear overlap / pooling
