@@ -1,27 +1,29 @@
 // K3: prior-weighted k-means (replaces kmeans(), batch_spalign_kmeans.py:136-183).
 //
-// One "sweep" streams the rows of X through shared memory in tiles of TR rows (cp.async,
-// double buffered) and does, per tile:
-//   phase 1   fp32 screening: thread (row, part) accumulates sum_d (x-c_k)^2 over its slice of
-//             the columns for every cluster k; centres (fp32 copies) are warp-wide broadcasts
-//   combine A warp 0: sums the slice partials, takes the fp32 argmin and proves it with a
-//             rigorous rounding-error bound; rows it cannot prove are listed as undecided
-//   exact     the whole block recomputes each undecided row in float64 (sqrt + NumPy argmin:
-//             first minimum, first NaN wins) -- exact ties and NaN centres land here
-//             (float64 inputs skip the screening and do phase 1 in float64)
-//   combine B warp 0: adopts the new assignment, omega = w or 1-w, stable grouping of the
-//             tile's rows by cluster; lane k keeps sum(omega), count and the virtual (x, y)
-//             column sums of cluster k, added in row order
-//   phase 2   centroid sums: thread t owns columns 2t, 2t+1 (+512, ...) and adds omega*x for the
-//             tile's rows cluster by cluster, in row order -> every accumulator is a plain
-//             sequential float64 sum, bit-reproducible
-// B200's FP64 pipe is ~1/8 of the FP32 rate, so float64 is kept to the places that decide the
-// result: the centroid sums and the undecided rows.
+// Building blocks (DESIGN.md section 4 has the measurements):
+//   screening   fp32, on differences of squared distances to cluster 0 (one subtraction and K
+//               FFMA per element); a row is decided only when a rigorous rounding-error bound
+//               separates the winner (km_screen_partial / km_screen_decide: fp32 decision
+//               with explicit error terms, then float64, then ...)
+//   exact pass  ... float64 distances with sqrt and NumPy's argmin rule (first minimum, first
+//               NaN wins) for the rows no bound can separate: exact ties, NaN centres
+//   sums        float64 centroid sums, thread t owns columns 2t, 2t+1 (+512, ...), rows added
+//               cluster by cluster in row order -> bit-reproducible; after the first full
+//               iteration only rows that changed cluster are moved (running sums)
+//   bounds      Hamerly upper/lower distance bounds per row, shifted by the centre drift; a
+//               sweep only gathers and screens the rows the bounds cannot prove stable
+// float64 is kept to the places that decide the result.  (DFMA runs at full rate on B200; it
+// is the F2F.F64.F32 conversions that are slow -- tools/fp64_probe.cu -- and a float64
+// distance pass is 2K flops per element on half the lanes of the fp32 screening.)
 //
-// Two drivers share the sweep: `kmeans_groups_kernel` (one persistent CTA per independent
-// problem, whole iteration loop on the device, no host sync) and `kmeans_sweep_kernel`
-// (one CTA per row chunk of a large problem; partials are summed in fixed chunk order by
-// `kmeans_reduce_kernel`, optionally all-reduced across GPUs, then `kmeans_update_kernel`).
+// Sweeps: km_sweep streams the rows of a chunk through shared memory in tiles (bulk copies on
+// mbarriers, double buffered; modes 0/1: init sums / full iteration; mode 3: move the listed
+// changed rows); km_sweep_sparse runs warp-independent pipelines over the rows a bounds pass
+// left active.  Kernels: kmeans_sweep_kernel (one CTA per row chunk; the chunk of a group
+// that arrives last reduces and updates -> one launch per iteration), kmeans_tail_kernel (one
+// persistent CTA per group runs all remaining iterations on-chip), kmeans_groups_kernel (one
+// persistent CTA per group, full sweeps; small problems), and the reduce / update kernels of
+// the three-step form that leaves room for an all-reduce.
 #include <stdlib.h>
 
 #include "common.cuh"
