@@ -1617,7 +1617,26 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       status = SPALIGN_KM_CONVERGED;
       break;
     }
-    // running sums += this iteration's moves; new centres and their drift
+    // running sums += this iteration's moves (thread-owned columns; issued first so that this
+    // global round trip overlaps the one of the per-cluster scalars below)
+#pragma unroll
+    for (int sl = 0; sl < NS2; ++sl) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 2 * (sl * KM_THREADS + t) + j;
+        if (c < Dr) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            if (k < K) {
+              const size_t idx = (size_t)k * (D + 2) + c;
+              acc[k][sl][j] += tt[idx];   // acc now holds the new running sum
+              tt[idx] = acc[k][sl][j];
+            }
+          }
+        }
+      }
+    }
+    // per-cluster scalars, new centres and their drift
     if (t < K) {
       double* e = tt + (size_t)t * (D + 2);
       const double ws = e[D] + xs[t * 4 + 0];
@@ -1658,10 +1677,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
             if (k < K) {
-              const size_t idx = (size_t)k * (D + 2) + c;
-              const double v = tt[idx] + acc[k][sl][j];
-              tt[idx] = v;
-              const double nv = v / s.extra[k * 4 + 0];
+              const double nv = acc[k][sl][j] / s.extra[k * 4 + 0];
               const double df = nv - s.cen[(size_t)k * Dc + c];
               q[k][0] = fma(df, df, q[k][0]);
               s.cen[(size_t)k * Dc + c] = nv;

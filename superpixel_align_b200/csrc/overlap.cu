@@ -559,7 +559,7 @@ scatter_kernel(OverlapWs ws, int cap_img, const int* __restrict__ indptr, int64_
 __global__ void __launch_bounds__(256)
 rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int* indices,
                     int* counts, int* area, double* sum_prior, double* wvals,
-                    const int64_t* __restrict__ nnz_flags) {
+                    const int64_t* __restrict__ nnz_flags, int ncell_hint) {
   if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
@@ -569,6 +569,78 @@ rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int
   if (L > WARP_TIER_MAX) return;
   int a_sum = 0;
   double* sorted_prior = ws.t_prior;  // pairs are dead after scatter
+  if (L <= 64 && ncell_hint <= (1 << 24)) {
+    // the common case: bitonic sort of (cell << 7 | position) keys, two per lane (elements
+    // lane and lane + 32), 21 compare-exchange stages; the payload is gathered afterwards
+    const unsigned PAD = 0xffffffffu;
+    unsigned k0 = lane < L ? ((unsigned)ws.u_col[base + lane] << 7) | (unsigned)lane : PAD;
+    unsigned k1 = lane + 32 < L
+                      ? ((unsigned)ws.u_col[base + lane + 32] << 7) | (unsigned)(lane + 32)
+                      : PAD;
+    if (L > 32) {
+#pragma unroll
+      for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          if (j == 32) {  // partner in the same lane (only in the last merge: ascending)
+            const unsigned lo = min(k0, k1), hi = max(k0, k1);
+            k0 = lo;
+            k1 = hi;
+          } else {
+            const unsigned p0 = __shfl_xor_sync(0xffffffffu, k0, j);
+            const unsigned p1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            const bool lower = (lane & j) == 0;
+            // element indices lane and lane + 32: direction bit from (index & k)
+            const bool up0 = (lane & k) == 0, up1 = ((lane + 32) & k) == 0;
+            k0 = (lower == up0) ? min(k0, p0) : max(k0, p0);
+            k1 = (lower == up1) ? min(k1, p1) : max(k1, p1);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned p0 = __shfl_xor_sync(0xffffffffu, k0, j);
+          const bool lower = (lane & j) == 0, up0 = (lane & k) == 0 || k == 32;
+          k0 = (lower == up0) ? min(k0, p0) : max(k0, p0);
+        }
+      }
+    }
+    double pv0 = 0.0, pv1 = 0.0;
+    if (lane < L) {
+      const int src = (int)(k0 & 127u);
+      const int cn = ws.u_cnt[base + src];
+      pv0 = ws.u_prior[base + src];
+      indices[base + lane] = (int)(k0 >> 7);
+      counts[base + lane] = cn;
+      sorted_prior[base + lane] = pv0;
+      if (wvals != nullptr) wvals[base + lane] = pv0;
+      a_sum += cn;
+    }
+    if (lane + 32 < L) {
+      const int src = (int)(k1 & 127u);
+      const int cn = ws.u_cnt[base + src];
+      pv1 = ws.u_prior[base + src];
+      indices[base + lane + 32] = (int)(k1 >> 7);
+      counts[base + lane + 32] = cn;
+      sorted_prior[base + lane + 32] = pv1;
+      if (wvals != nullptr) wvals[base + lane + 32] = pv1;
+      a_sum += cn;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
+    if (lane == 0) area[r] = a_sum;
+    if (sum_prior != nullptr) {  // same order as the general path: lane, lane + 32, then the tree
+      double ps = __dadd_rn(0.0, pv0);
+      if (lane + 32 < L) ps = __dadd_rn(ps, pv1);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, d));
+      if (lane == 0) sum_prior[r] = ps;
+    }
+    return;
+  }
   for (int a = 0; a < L; a += 32) {
     const int e = a + lane;
     const bool valid = e < L;
@@ -784,7 +856,7 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
   rowsort_warp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
-      ws, indptr, n_rows, indices, counts, area, sum_prior, nullptr, nnz_flags);
+      ws, indptr, n_rows, indices, counts, area, sum_prior, nullptr, nnz_flags, ncell);
   rowsort_heavy_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(ws, indptr, ncell, indices,
                                                                  counts, area, sum_prior,
                                                                  nullptr, nnz_flags);
@@ -856,7 +928,7 @@ extern "C" int spalign_overlap_bilinear_csr(
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
   rowsort_warp_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
-      ws, indptr, n_rows, indices, counts, area, sum_prior, wvals, nnz_flags);
+      ws, indptr, n_rows, indices, counts, area, sum_prior, wvals, nnz_flags, ncell);
   rowsort_heavy_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(ws, indptr, ncell, indices,
                                                                  counts, area, sum_prior, wvals,
                                                                  nnz_flags);
