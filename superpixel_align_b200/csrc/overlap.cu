@@ -243,11 +243,12 @@ emit_s8_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
         continue;
       }
       const int cnt = __popc(lo) + __popc(hi);
-      int syl = 0, sxl = 0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) syl += r * __popc((unsigned)(m >> (8 * r)) & 0xffu);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sxl += j * __popcll((m >> j) & 0x0101010101010101ull);
+      // sum of the row (column) indices of the set bits: bit i sits in row i >> 3, column
+      // i & 7, so each index bit contributes 2^b * popc(m & {bits whose index has bit b set})
+      const int sxl = __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) +
+                      4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull);
+      const int syl = __popcll(m & 0xff00ff00ff00ff00ull) + 2 * __popcll(m & 0xffff0000ffff0000ull) +
+                      4 * __popcll(m & 0xffffffff00000000ull);
       double pr = 0.0;
       if (have_prior) {
         if (remaining == 0ull && can_complement) {

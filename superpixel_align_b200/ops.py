@@ -558,6 +558,9 @@ class KMeansLarge:
                 _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_finish')
             _count('kmeans_finish')
             return KMeansResult(self.assign, self.iters, self.status, self.centers)
+        if self.allreduce is not None:
+            # every rank must enqueue the same number of collectives: poll at fixed iterations
+            blocking = True
         done = 0
         nxt = min(first_poll, self.n_iter)
         pending = None
