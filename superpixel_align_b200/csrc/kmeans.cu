@@ -55,6 +55,7 @@ __device__ unsigned long long g_km_prof2[8];
 __device__ unsigned long long g_km_prof4[16];
 __device__ unsigned long long g_km_prof3[8];
 __device__ unsigned long long g_km_slow;
+__device__ unsigned long long g_km_trace[3 * 1024];  // per group: start ns, end ns, iterations
 #define KM_TICK3(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof3__[i] += now__ - last3__; last3__ = now__; } } while (0)
 #define KM_TICK2(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof2__[i] += now__ - last2__; last2__ = now__; } } while (0)
 #define KM_TICK(i) do { if (threadIdx.x == 0) { long long now__ = clock64(); prof__[i] += now__ - last__; last__ = now__; } } while (0)
@@ -650,7 +651,6 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
     const int tb = ti * TR;                          // index of the tile's first row in the
     const int nvalid = min(TR, nrows - tb);          // (possibly compacted) row list
     const unsigned gt = tile_base + (unsigned)ti;   // tile counter across sweeps
-    if (t == 0) *s.namb = 0;
     // every warp keeps the old assignment / prior weight of tile row `lane` (L2 hits)
     // (mode 2 uses two lanes per row: lane r adds row r to its new cluster, lane TR + r
     // removes it from the old one)
@@ -669,6 +669,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
       if (mode != 0) pre_w = a.w[KM_ROW(prow)];
     }
     __syncthreads();  // (A) all warps are past phase 2 of tile ti-1: its buffer is free
+    if (t == 0) *s.namb = 0;  // (read by every warp before this barrier, filled after the next)
     KM_TICK(0);
     if (ti + 1 < ntiles && t < 32)  // prefetch the next tile into the buffer just released
       issue_tile<XT>(a, s.buf0 + (size_t)((gt + 1) & 1) * s.tile_bytes, s.bar + ((gt + 1) & 1),
@@ -1581,6 +1582,13 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   __syncthreads();
   int it = g.iters[grp];
   int status = SPALIGN_KM_ITER_CAP;
+#ifdef KM_PROFILE
+  if (t == 0 && grp < 1024) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    g_km_trace[grp * 3] = ns;
+  }
+#endif
   unsigned tile_base = 0, wtile = 0;
   bool first = true;
   double acc[KT][NS2][2];
@@ -1783,6 +1791,14 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   if (t == 0) {
     g.iters[grp] = it;
     g.status[grp] = status;
+#ifdef KM_PROFILE
+    if (grp < 1024) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+      g_km_trace[grp * 3 + 1] = ns;
+      g_km_trace[grp * 3 + 2] = (unsigned long long)it;
+    }
+#endif
   }
 }
 
@@ -2182,6 +2198,30 @@ extern "C" int spalign_kmeans_debug_stats(int64_t* out_host, int reset) {
       cudaMemcpyFromSymbol(&slow, g_km_slow, sizeof(slow));
       cudaMemcpyToSymbol(g_km_slow, &zero, sizeof(zero));
       fprintf(stderr, "[km_profile] rows that took the float64 decision path: %llu\n", slow);
+    }
+    {
+      static unsigned long long tr[3 * 1024];
+      cudaMemcpyFromSymbol(tr, g_km_trace, sizeof(tr));
+      unsigned long long t0 = ~0ull, t1 = 0;
+      int n = 0;
+      for (int g = 0; g < 1024; ++g)
+        if (tr[g * 3 + 1]) { ++n; if (tr[g * 3] < t0) t0 = tr[g * 3]; if (tr[g * 3 + 1] > t1) t1 = tr[g * 3 + 1]; }
+      if (n) {
+        fprintf(stderr, "[km_profile] finish kernel trace: %d groups, span %.1f us; per group (start us, run us, iterations), sorted by end:\n", n, (t1 - t0) / 1e3);
+        // print the 12 groups that end last and a few aggregate numbers
+        double sum_run = 0; int late = 0;
+        for (int g = 0; g < 1024; ++g) if (tr[g * 3 + 1]) { sum_run += (tr[g * 3 + 1] - tr[g * 3]) / 1e3; if (tr[g * 3] - t0 > 20000) ++late; }
+        fprintf(stderr, "[km_profile]   mean run %.1f us, groups that started > 20 us late: %d\n", sum_run / n, late);
+        for (int k = 0; k < 12; ++k) {
+          int best = -1;
+          for (int g = 0; g < 1024; ++g) if (tr[g * 3 + 1] && (best < 0 || tr[g * 3 + 1] > tr[best * 3 + 1])) best = g;
+          if (best < 0) break;
+          fprintf(stderr, "[km_profile]   group %d: start %.1f run %.1f iters %llu (%.1f us/iter)\n", best, (tr[best * 3] - t0) / 1e3, (tr[best * 3 + 1] - tr[best * 3]) / 1e3, tr[best * 3 + 2], (tr[best * 3 + 1] - tr[best * 3]) / 1e3 / (tr[best * 3 + 2] > 1 ? tr[best * 3 + 2] - 1 : 1));
+          tr[best * 3 + 1] = 0;
+        }
+      }
+      static unsigned long long zz[3 * 1024];
+      cudaMemcpyToSymbol(g_km_trace, zz, sizeof(zz));
     }
     cudaMemcpyFromSymbol(p, g_km_prof3, sizeof(p));
     if (p[7])
