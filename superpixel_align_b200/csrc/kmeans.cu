@@ -86,6 +86,7 @@ struct KmArgs {
   float* lb;          // [N] Hamerly lower bound: distance to the closest other centre
   int Kc;             // clusters the kernel variant is unrolled for (>= K)
   int part_bytes;     // size of the phase-1 partial-sum scratch
+  int buf_rows;       // rows per half of the tile / row-buffer region (>= TR)
 };
 
 // shared-memory carve-up (all offsets from the dynamic smem base)
@@ -114,11 +115,13 @@ struct KmSmem {
 };
 
 __host__ __device__ inline size_t km_carve(KmSmem* s, char* base, int TR, int srow, int K,
-                                           int Dc, int Kc, int part_bytes) {
+                                           int Dc, int Kc, int part_bytes, int buf_rows = 0) {
   size_t o = 0;
   const size_t tile = (size_t)TR * srow;
   if (s) { s->buf0 = base; s->tile_bytes = (int)tile; }
-  o += 2 * tile + 32;
+  // two tiles of TR rows; the sparse sweep's per-warp row buffers (8 warps x 2 x R rows) share
+  // the region and may need more
+  o += 2 * (buf_rows > TR ? (size_t)buf_rows * srow : tile) + 32;
   o = (o + 15) & ~(size_t)15;
   if (s) s->cen = reinterpret_cast<double*>(base + o);
   o += (size_t)K * Dc * sizeof(double);
@@ -289,6 +292,7 @@ __device__ __forceinline__ float km_screen_partial(const KmArgs& a, const KmSmem
 #pragma unroll
     for (int k = 0; k < KT; ++k) a1[r][k] = 0.f;
   const int main_d = a.Dm;
+#pragma unroll(R == 4 ? 2 : 1)
   for (int d = lane * 4; d < main_d; d += 128) {
     const float4 c0v = *reinterpret_cast<const float4*>(s.cen32 + d);
     float4 df[R];
@@ -986,7 +990,7 @@ __device__ __forceinline__ void km_sweep_sparse(const KmArgs& a, const KmSmem s,
   const char* Xb = reinterpret_cast<const char*>(a.X);
   char* wbuf = s.buf0 + (size_t)wq * 2 * R * a.srow;          // this warp's two R-row buffers
   const int nsets = (na + R - 1) / R;                          // sets of R list entries
-  constexpr int BR = 16;                                       // rows per decision batch
+  constexpr int BR = R == 4 ? 32 : 16;                         // rows per decision batch
   constexpr int SPB = BR / R;
   __shared__ float stF[KM_THREADS / 32][BR * KT];
   __shared__ float stX[KM_THREADS / 32][BR * KM_NTAIL];
@@ -1314,7 +1318,7 @@ template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes, g.a.buf_rows);
   const int grp = blockIdx.x;
   const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
   const int t = threadIdx.x;
@@ -1435,7 +1439,7 @@ template <typename XT, int KT, int NS2, int R, int MINB>
 __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(128) char smem_raw[];
   KmSmem s;
-  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes, g.a.buf_rows);
   // chunks are listed in launch order (large ones first); column 3 is the chunk's slot in the
   // group-contiguous, row-ordered partials array that the reduction walks
   const int grp = (int)g.chunks[(size_t)blockIdx.x * 4];
@@ -1563,7 +1567,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   extern __shared__ __align__(128) char smem_raw[];
   if (sizeof(XT) != 4) return;  // host side refuses float64 rows
   KmSmem s;
-  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes);
+  km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes, g.a.buf_rows);
   const int grp = blockIdx.x;
   if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
@@ -1911,10 +1915,11 @@ struct Plan {
   int Dc;
   int Kc;
   int part_bytes;
+  int buf_rows;
   size_t smem;
 };
 
-bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p, int max_tr = 32) {
+bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p, int max_tr = 32, int sparse_r = 0) {
   const int es = x_dtype == SPALIGN_F32 ? 4 : 8;
   const int row_bytes = (int)align_up((size_t)Dr * es, 16);
   int srow = row_bytes;
@@ -1927,6 +1932,17 @@ bool make_plan(int x_dtype, int D, int Dr, int K, Plan* p, int max_tr = 32) {
   p->variant = x_dtype == SPALIGN_F64 ? 2 : (small ? 0 : 1);
   const size_t limit = (size_t)200 * 1024;
   p->Kc = small ? 4 : 8;
+  p->buf_rows = 0;
+  if (sparse_r == 4 && small) {
+    // finish kernel, latency over occupancy: the warps of the sparse sweep take 4 rows per set
+    // (one CTA per SM); the tiles that move changed rows keep 16 rows
+    const int pb = (KM_THREADS / 32) * (4 * p->Kc) * 33 * (int)sizeof(float);
+    const size_t bytes = km_carve(nullptr, nullptr, 16, srow, K, p->Dc, p->Kc, pb, 32);
+    if (bytes <= limit) {
+      p->R = 4; p->TR = 16; p->logTR = 4; p->part_bytes = pb; p->buf_rows = 32; p->smem = bytes;
+      return true;
+    }
+  }
   if (p->variant == 2) {
     for (int tr = 32, lg = 5; tr >= 2; tr >>= 1, --lg) {
       const int pb = KM_THREADS * p->Kc * (int)sizeof(double);
@@ -1982,6 +1998,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->Dm = (Dr % 4 == 2) ? Dr - 2 : (Dr & ~3);
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
+  a->buf_rows = p.buf_rows;
   a->ub = nullptr; a->lb = nullptr;
   return SPALIGN_OK;
 }
@@ -2117,7 +2134,9 @@ extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, in
   SPALIGN_REQUIRE(x_dtype == SPALIGN_F32, "kmeans_finish: fp32 rows only");
   Plan plan;
   const int Dr = D - (pos_mode ? 2 : 0);
-  if (!make_plan(x_dtype, D, Dr, K, &plan, 16)) {
+  int sparse_r = 4;
+  if (const char* e = getenv("SPALIGN_KM_TAIL_R")) sparse_r = atoi(e);
+  if (!make_plan(x_dtype, D, Dr, K, &plan, 16, sparse_r)) {
     set_error("kmeans_finish: D=%d does not fit shared memory", D);
     return SPALIGN_E_UNSUPPORTED;
   }
