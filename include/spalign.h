@@ -212,12 +212,19 @@ int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode
  * are current.  group_off: device int64[G+1] row ranges.  Same stop rules and results as
  * repeating spalign_kmeans_iterate (batch_spalign_kmeans.py:152-179); meant for many groups
  * of at most a few thousand rows each (per-image clustering), where it replaces one launch
- * and one host poll per iteration. */
+ * and one host poll per iteration.
+ * slice_iters > 0: every group runs at most that many iterations in this launch and is left
+ * SPALIGN_KM_RUNNING if it has not stopped (all state is in the global arrays; a later call
+ * continues).  rows_per_set: rows each warp of the sparse sweep takes at a time -- 2: two CTAs
+ * per SM (all of up to 2 x #SM groups resident, each slower), 4 (= 0, default): one CTA per SM,
+ * ~1.5x faster per group (24 vs 37 us per iteration of a slow image; the single 4-row launch
+ * is also the faster schedule at 300 groups on 148 SMs). */
 int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
                           int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
                           const int64_t* group_off, int G, int n_iter, int32_t* assign,
                           double* totals, double* centers, int32_t* iters, int32_t* status,
-                          float* ub, float* lb, double* cdelta, spalign_stream_t stream);
+                          float* ub, float* lb, double* cdelta, int slice_iters, int rows_per_set,
+                          spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

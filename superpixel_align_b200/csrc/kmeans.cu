@@ -1554,6 +1554,7 @@ struct TailArgs {
   int32_t* status;
   double* cdelta;            // [G][K]
   int n_iter;
+  int slice;                 // iterations to run in this launch (0: until the group stops)
 };
 
 // Remaining iterations of one group by one persistent CTA (fp32 rows, after the first full
@@ -1595,6 +1596,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
 #endif
   unsigned tile_base = 0, wtile = 0;
   bool first = true;
+  int done_here = 0;
   double acc[KT][NS2][2];
 #ifdef KM_PROFILE
   long long prof2__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1782,6 +1784,10 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       s.hk[0] = m;
     }
     KM_TICK2(3);
+    if (g.slice > 0 && ++done_here >= g.slice && it < g.n_iter) {
+      status = SPALIGN_KM_RUNNING;  // paused: a later launch continues from the global state
+      break;
+    }
   }
   __syncthreads();
 #ifdef KM_PROFILE
@@ -2126,16 +2132,17 @@ extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, in
                                      const double* w, int D, int K, const int64_t* group_off,
                                      int G, int n_iter, int32_t* assign, double* totals,
                                      double* centers, int32_t* iters, int32_t* status, float* ub,
-                                     float* lb, double* cdelta, spalign_stream_t stream_) {
+                                     float* lb, double* cdelta, int slice_iters,
+                                     int rows_per_set, spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPALIGN_REQUIRE(group_off && assign && totals && centers && iters && status && ub && lb &&
-                      cdelta && G > 0 && n_iter >= 0,
+                      cdelta && G > 0 && n_iter >= 0 && slice_iters >= 0 &&
+                      (rows_per_set == 0 || rows_per_set == 2 || rows_per_set == 4),
                   "kmeans_finish: bad arguments");
   SPALIGN_REQUIRE(x_dtype == SPALIGN_F32, "kmeans_finish: fp32 rows only");
   Plan plan;
   const int Dr = D - (pos_mode ? 2 : 0);
-  int sparse_r = 4;
-  if (const char* e = getenv("SPALIGN_KM_TAIL_R")) sparse_r = atoi(e);
+  const int sparse_r = rows_per_set == 0 ? 4 : rows_per_set;
   if (!make_plan(x_dtype, D, Dr, K, &plan, 16, sparse_r)) {
     set_error("kmeans_finish: D=%d does not fit shared memory", D);
     return SPALIGN_E_UNSUPPORTED;
@@ -2145,7 +2152,7 @@ extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, in
   if (rc) return rc;
   g.a.ub = ub; g.a.lb = lb;
   g.group_off = group_off; g.assign = assign; g.totals = totals; g.centers = centers;
-  g.iters = iters; g.status = status; g.cdelta = cdelta; g.n_iter = n_iter;
+  g.iters = iters; g.status = status; g.cdelta = cdelta; g.n_iter = n_iter; g.slice = slice_iters;
   KM_DISPATCH(kmeans_tail_kernel, g, G);
   return check_launch("kmeans_finish");
 }

@@ -6,6 +6,8 @@ Nothing in this module synchronises unless its docstring says so.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -401,7 +403,7 @@ class KMeansLarge:
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
-                 incremental=True, bounds=True, tail=True, tail_after=1):
+                 incremental=True, bounds=True, tail=True, tail_after=1, tail_slice=0):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -444,6 +446,7 @@ class KMeansLarge:
                      (max_rows <= self.TAIL_ROWS or
                       (max_rows <= 8 * self.TAIL_ROWS and self.G >= 148)))
         self.tail_after = tail_after
+        self.tail_slice = tail_slice
         if self.tail:
             self.goff_dev = torch.from_numpy(self.goff).to(dev, non_blocking=True)
         self._lib = _lib.load()
@@ -550,13 +553,21 @@ class KMeansLarge:
         if self.tail and self.n_iter > 0:
             for _ in range(min(self.tail_after, self.n_iter)):
                 self._sweep(1)
-            check(self._lib.spalign_kmeans_finish(
-                _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
-                self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K,
-                _ptr(self.goff_dev), self.G, self.n_iter, _ptr(self.assign), _ptr(self.totals),
-                _ptr(self.centers), _ptr(self.iters), _ptr(self.status), _ptr(self.ub),
-                _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_finish')
-            _count('kmeans_finish')
+            # default: one launch, one CTA per SM (4 rows per warp set).  tail_slice > 0 first
+            # runs that many iterations with every group resident (2 CTAs per SM, 2 rows per
+            # set), then the rest -- measured no faster at 300 groups (profiles/README.md)
+            plan = [(0, 4)]
+            if self.tail_slice > 0:
+                plan = [(self.tail_slice, 2), (0, 4)]
+            for slice_iters, rows in plan:
+                check(self._lib.spalign_kmeans_finish(
+                    _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
+                    self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K,
+                    _ptr(self.goff_dev), self.G, self.n_iter, _ptr(self.assign),
+                    _ptr(self.totals), _ptr(self.centers), _ptr(self.iters), _ptr(self.status),
+                    _ptr(self.ub), _ptr(self.lb), _ptr(self.cdelta), slice_iters, rows,
+                    _stream()), 'kmeans_finish')
+                _count('kmeans_finish')
             return KMeansResult(self.assign, self.iters, self.status, self.centers)
         if self.allreduce is not None:
             # every rank must enqueue the same number of collectives: poll at fixed iterations

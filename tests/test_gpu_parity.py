@@ -525,6 +525,10 @@ def test_kmeans_finish_kernel_equals_per_iteration_launches(ops, sizes, tail_row
     b = ops.KMeansLarge(*args, tail=False).run()
     assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
     assert torch.equal(a.status, b.status)
+    # paused after 3 iterations (2 rows per warp set, 2 CTAs per SM), continued by a second launch
+    c = ops.KMeansLarge(*args, tail_slice=3).run()
+    assert torch.equal(a.assign, c.assign) and torch.equal(a.iters, c.iters)
+    assert torch.equal(a.status, c.status)
     for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
         if a.status[g].item() == 0:        # centres of converged groups: same up to summation order
             torch.testing.assert_close(a.centers[g], b.centers[g], rtol=1e-10, atol=1e-10)

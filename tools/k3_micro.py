@@ -27,7 +27,8 @@ init = torch.randint(0, 4, (N,), generator=g, device=dev, dtype=torch.int32)
 goff = np.arange(G + 1) * S
 Xv = X[:, :514]
 KW = dict(tail=os.environ.get('K3_TAIL', '1') == '1',
-          tail_after=int(os.environ.get('K3_TAIL_AFTER', '1')))
+          tail_after=int(os.environ.get('K3_TAIL_AFTER', '1')),
+          tail_slice=int(os.environ.get('K3_SLICE', '0')))
 for _ in range(2):
     res = ops.KMeansLarge(Xv, w, init, 4, goff, **KW).run()
 torch.cuda.synchronize()
