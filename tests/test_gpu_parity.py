@@ -538,6 +538,27 @@ def test_kmeans_finish_kernel_equals_per_iteration_launches(ops, sizes, tail_row
         assert a.iters[g].item() == info['iters'] and a.status[g].item() == info['status']
 
 
+@pytest.mark.parametrize('D,K', [(66, 8), (1026, 3), (7, 2), (512, 4), (100, 5)])
+def test_kmeans_finish_kernel_other_shapes(ops, D, K):
+    # kernel variants behind the finish kernel: K > 4 and rows > 1024 columns (2 rows per warp
+    # set), short rows, row lengths without centroid columns, more than 3 float64 tail columns
+    rs = np.random.RandomState(D + K)
+    sizes = [700, 33, 1200]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = _blobs(rs, off[-1], D, K, spread=1.0)
+    w = rs.uniform(0, 1, len(X))
+    init = np.concatenate([so.kmeans_init(K, w[a:b], rng=rs) for a, b in zip(off[:-1], off[1:])]).astype(np.int32)
+    km = ops.KMeansLarge(torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()),
+                         torch.from_numpy(init).to(dev()), K, off)
+    assert km.tail
+    res = km.run()
+    for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        want, info = so.kmeans(K, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64),
+                               return_info=True, verbose=False)
+        assert np.array_equal(res.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
+        assert res.iters[g].item() == info['iters'] and res.status[g].item() == info['status']
+
+
 def test_kmeans_finish_kernel_iteration_cap(ops):
     rs = np.random.RandomState(5)
     X = _blobs(rs, 1500, 66, 4, spread=0.4)   # heavily overlapping blobs: many iterations
