@@ -87,6 +87,7 @@ struct KmArgs {
   int Kc;             // clusters the kernel variant is unrolled for (>= K)
   int part_bytes;     // size of the phase-1 partial-sum scratch
   int buf_rows;       // rows per half of the tile / row-buffer region (>= TR)
+  int xcols;          // last stored columns (<= 2) summed with the per-cluster scalars, not in phase 2
 };
 
 // shared-memory carve-up (all offsets from the dynamic smem base)
@@ -898,6 +899,10 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
               virtual_pos(a, KM_ROW(ent & 0xff), &px, &py);
               e_x = fma(o, px, e_x);
               e_y = fma(o, py, e_y);
+            } else if (a.xcols) {  // the last stored columns (see fill_args)
+              const XT* xr = reinterpret_cast<const XT*>(tile + (size_t)(ent & 0xff) * a.srow);
+              e_x = fma(o, (double)xr[Dr - a.xcols], e_x);
+              if (a.xcols == 2) e_y = fma(o, (double)xr[Dr - 1], e_y);
             }
           }
         }
@@ -906,10 +911,11 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
 
     KM_TICK(3);
     // ---- phase 2: centroid sums, cluster by cluster, rows in order ----
+    const int Dp = Dr - a.xcols;  // columns summed here
 #pragma unroll
     for (int sl = 0; sl < NS2; ++sl) {
       const int c0 = 2 * (sl * KM_THREADS + t);
-      if (c0 + 1 < Dr) {
+      if (c0 + 1 < Dp) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           if (k < K) {
@@ -934,7 +940,7 @@ __device__ __forceinline__ void km_sweep(const KmArgs& a, const KmSmem s, int64_
             }
           }
         }
-      } else if (c0 < Dr) {
+      } else if (c0 < Dp) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           if (k < K) {
@@ -1200,14 +1206,18 @@ __device__ __forceinline__ bool finalize_centers(const KmArgs& a, const KmSmem s
     for (int k = 0; k < KT; ++k) {
       if (k < K) {
         const double ws = s.extra[k * 4 + 0];
-        if (c0 < Dr) s.cen[(size_t)k * a.Dc + c0] = acc[k][sl][0] / ws;
-        if (c0 + 1 < Dr) s.cen[(size_t)k * a.Dc + c0 + 1] = acc[k][sl][1] / ws;
+        if (c0 < Dr - a.xcols) s.cen[(size_t)k * a.Dc + c0] = acc[k][sl][0] / ws;
+        if (c0 + 1 < Dr - a.xcols) s.cen[(size_t)k * a.Dc + c0 + 1] = acc[k][sl][1] / ws;
       }
     }
   }
   if (a.pos_mode && t < K) {
     s.cen[(size_t)t * a.Dc + Dr] = s.extra[t * 4 + 2] / s.extra[t * 4 + 0];
     s.cen[(size_t)t * a.Dc + Dr + 1] = s.extra[t * 4 + 3] / s.extra[t * 4 + 0];
+  }
+  if (a.xcols && t < K) {
+    for (int i = 0; i < a.xcols; ++i)
+      s.cen[(size_t)t * a.Dc + Dr - a.xcols + i] = s.extra[t * 4 + 2 + i] / s.extra[t * 4 + 0];
   }
   bool empty = false;
   for (int k = 0; k < K; ++k) empty |= (s.extra[k * 4 + 1] == 0.0);
@@ -1493,8 +1503,8 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
       if (k < K) {
-        if (c0 < Dr) out[(size_t)k * (D + 2) + c0] = acc[k][sl][0];
-        if (c0 + 1 < Dr) out[(size_t)k * (D + 2) + c0 + 1] = acc[k][sl][1];
+        if (c0 < Dr - g.a.xcols) out[(size_t)k * (D + 2) + c0] = acc[k][sl][0];
+        if (c0 + 1 < Dr - g.a.xcols) out[(size_t)k * (D + 2) + c0 + 1] = acc[k][sl][1];
       }
     }
   }
@@ -1503,6 +1513,8 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
       out[(size_t)t * (D + 2) + Dr] = s.extra[t * 4 + 2];
       out[(size_t)t * (D + 2) + Dr + 1] = s.extra[t * 4 + 3];
     }
+    for (int i = 0; i < g.a.xcols; ++i)
+      out[(size_t)t * (D + 2) + Dr - g.a.xcols + i] = s.extra[t * 4 + 2 + i];
     out[(size_t)t * (D + 2) + D] = s.extra[t * 4 + 0];
     out[(size_t)t * (D + 2) + D + 1] = s.extra[t * 4 + 1];
   }
@@ -1638,7 +1650,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = 2 * (sl * KM_THREADS + t) + j;
-        if (c < Dr) {
+        if (c < Dr - g.a.xcols) {
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
             if (k < K) {
@@ -1668,6 +1680,15 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
         s.cen[(size_t)t * Dc + Dr] = nx;
         s.cen[(size_t)t * Dc + Dr + 1] = ny;
       }
+      for (int i = 0; i < g.a.xcols; ++i) {  // the last stored columns travel with the scalars
+        const int c = Dr - g.a.xcols + i;
+        const double v = e[c] + xs[t * 4 + 2 + i];
+        e[c] = v;
+        const double nv = v / ws;
+        const double df = nv - s.cen[(size_t)t * Dc + c];
+        dp = fma(df, df, dp);
+        s.cen[(size_t)t * Dc + c] = nv;
+      }
       s.extra[t * 4 + 0] = ws;
       s.extra[t * 4 + 1] = cnt;
       s.extra[t * 4 + 2] = dp;
@@ -1685,7 +1706,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = 2 * (sl * KM_THREADS + t) + j;
-        if (c < Dr) {
+        if (c < Dr - g.a.xcols) {
           const bool mainc = c < g.a.Dm;
           double cn0 = 0.0;
 #pragma unroll
@@ -1739,6 +1760,10 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
         if (g.a.pos_mode) {
           const double px = s.cen[(size_t)t * Dc + Dr], py = s.cen[(size_t)t * Dc + Dr + 1];
           c2s = fma(px, px, fma(py, py, c2s));
+        }
+        for (int i = 0; i < g.a.xcols; ++i) {
+          const double cv = s.cen[(size_t)t * Dc + Dr - g.a.xcols + i];
+          c2s = fma(cv, cv, c2s);
         }
       }
       if (t == 0) s.cnorm[0] = (float)sqrt(c2ms) * 1.0001f;
@@ -2005,6 +2030,11 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
   a->buf_rows = p.buf_rows;
+  // Thread t of phase 2 owns columns 2t, 2t+1 (+512, ...).  A row of 512n + 1 or 512n + 2 stored
+  // columns (the 514-column descriptors) would leave one thread -- and with it its whole warp --
+  // a second pass over every list entry for those last columns alone; they are summed by the
+  // lanes that keep the per-cluster scalars instead (same accumulation order, same bits).
+  a->xcols = (!pos_mode && Dr > 2 * KM_THREADS && Dr % (2 * KM_THREADS) <= 2) ? Dr % (2 * KM_THREADS) : 0;
   a->ub = nullptr; a->lb = nullptr;
   return SPALIGN_OK;
 }
