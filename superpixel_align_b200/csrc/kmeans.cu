@@ -2030,12 +2030,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->D = D; a->Dr = Dr; a->Dc = p.Dc; a->K = K; a->srow = p.srow; a->copy16 = p.copy16;
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
   a->buf_rows = p.buf_rows;
-  // Thread t of phase 2 owns columns 2t, 2t+1 (+512, ...).  A row of 512n + 1 or 512n + 2 stored
-  // columns (the 514-column descriptors) would leave one thread -- and with it its whole warp --
-  // a second pass over every list entry for those last columns alone; they are summed by the
-  // lanes that keep the per-cluster scalars instead (same accumulation order, same bits).
-  a->xcols = (!pos_mode && Dr > 2 * KM_THREADS && Dr % (2 * KM_THREADS) <= 2) ? Dr % (2 * KM_THREADS) : 0;
-  a->ub = nullptr; a->lb = nullptr;
+  a->xcols = 0;
   return SPALIGN_OK;
 }
 
@@ -2181,6 +2176,14 @@ extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, in
   int rc = fill_args(&g.a, plan, X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K);
   if (rc) return rc;
   g.a.ub = ub; g.a.lb = lb;
+  // Thread t of phase 2 owns columns 2t, 2t+1 (+512, ...).  A row of 512n + 1 or 512n + 2 stored
+  // columns (the 514-column descriptors) leaves one thread -- and with it its whole warp -- a
+  // second pass over every list entry for those last columns alone.  When only the short
+  // changed-row tiles of the finish kernel run, they are summed by the lanes that keep the
+  // per-cluster scalars instead (same accumulation order, same bits); in the full sweeps that
+  // serial loop would cost more than the second pass (measured), so only here.
+  g.a.xcols = (!pos_mode && Dr > 2 * KM_THREADS && Dr % (2 * KM_THREADS) <= 2)
+                  ? Dr % (2 * KM_THREADS) : 0;
   g.group_off = group_off; g.assign = assign; g.totals = totals; g.centers = centers;
   g.iters = iters; g.status = status; g.cdelta = cdelta; g.n_iter = n_iter; g.slice = slice_iters;
   KM_DISPATCH(kmeans_tail_kernel, g, G);
