@@ -2031,6 +2031,7 @@ int fill_args(KmArgs* a, const Plan& p, const void* X, int x_dtype, int64_t ldx,
   a->TR = p.TR; a->logTR = p.logTR; a->Kc = p.Kc; a->part_bytes = p.part_bytes;
   a->buf_rows = p.buf_rows;
   a->xcols = 0;
+  a->ub = nullptr; a->lb = nullptr;
   return SPALIGN_OK;
 }
 
