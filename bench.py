@@ -346,6 +346,11 @@ def run_ours(args):
     if rank == 0 or world > 1:
         e2e = run_e2e(args, dev, labels, feats, world)
 
+    # ---- configs[4]: dataset-wide clustering of the pooled descriptors ----
+    gk = None
+    if not args.no_global_kmeans:
+        gk = run_global_kmeans(args, dev, out, world, rank, n_img)
+
     # ---- CPU baseline: oracle port on the host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,12 +378,124 @@ def run_ours(args):
                        'status_counts': {str(s): int((status == s).sum()) for s in np.unique(status)},
                        'init_tie_groups': tie_groups,
                        'rows_screened_fp32': screened, 'rows_exact_f64': exact_rows},
-            'nnz_per_image': nnz / n_img, 'setup_s': t_setup,
+            'global_kmeans': gk, 'nnz_per_image': nnz / n_img, 'setup_s': t_setup,
             'us_per_image': 1000.0 * ms_max / args.steps / n_img,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_global_kmeans(args, dev, out, world, rank, n_img):
+    """BASELINE configs[4]: ONE prior-weighted k-means over the pooled descriptors of all ranks
+    (rows sharded contiguously, rank r holds its 300 images' superpixels).  Timed with CUDA
+    events around the device work of a whole run (init sums + all iterations), max over ranks:
+    'peer' = exchange inside the iterate kernel over NVLink peer memory (one launch per
+    iteration), 'nccl' = sweep/reduce/all_reduce/update (the baseline), 'local' = this rank's rows
+    alone without any exchange.  A reduced problem (2 images per rank) is checked against the
+    CPU oracle's kmeans() on the concatenated matrix in the same run."""
+    import torch
+    import torch.distributed as dist
+    from superpixel_align_b200 import dist_kmeans, ops, _lib
+    X, w = out.features, out.weights
+    N_local, D = X.shape
+    pv = K * (D + 2) + 1
+    res = {'rows_per_gpu': int(N_local), 'rows_total': int(N_local) * world, 'columns': int(D),
+           'K': K, 'exchange_doubles_per_iteration': pv}
+
+    def host_init(wh):
+        n = len(wh)
+        init = np.zeros(n, dtype=np.int32)
+        thr = float(np.sort(wh)[n // 2])
+        low = wh <= thr
+        idx = np.arange(int(low.sum())) % (K - 1) + 1
+        np.random.shuffle(idx)
+        init[low] = idx
+        return init
+
+    def timed(fn, reps=3):
+        best = None
+        for _ in range(reps):
+            ev = []
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            r = fn(ev)
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            if best is None or ms < best[0]:
+                best = (ms, r)
+        ms, r = best
+        it = int(r.iters[0].item())
+        return {'ms': ms, 'iterations': it, 'us_per_iteration': 1e3 * ms / max(1, it),
+                'status': int(r.status[0].item())}
+
+    # this rank's rows alone (what N = 1 pays per iteration for the same rows per GPU)
+    np.random.seed(1111)
+    init_l = torch.from_numpy(host_init(w.cpu().numpy())).to(dev)
+
+    def local(ev):
+        km = ops.KMeansLarge(X, w, init_l, K, [0, N_local])
+        return dist_kmeans._timed_run(km, 4, ev)
+    res['local'] = timed(local)
+    if world == 1:
+        return res
+    np.random.seed(1111)
+    init_g = dist_kmeans.distributed_init(w.cpu().numpy(), K)
+    row0 = rank * N_local
+    comm = dist_kmeans.PeerComm(pv)
+    res['peer'] = timed(lambda ev: dist_kmeans.global_kmeans(
+        X, w, K, init_local=init_g, exchange='peer', comm=comm, row0=row0, events=ev))
+    res['nccl'] = timed(lambda ev: dist_kmeans.global_kmeans(
+        X, w, K, init_local=init_g, exchange='nccl', row0=row0, events=ev))
+    # the all-reduce alone: pv float64 values, back to back
+    buf = torch.zeros(pv, dtype=torch.float64, device=dev)
+    for _ in range(5):
+        dist.all_reduce(buf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(50):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    res['nccl_allreduce_us'] = 1e3 * e0.elapsed_time(e1) / 50
+    res['nccl']['pct_in_allreduce'] = 100.0 * res['nccl_allreduce_us'] / res['nccl']['us_per_iteration']
+    res['peer_vs_local_us_per_iteration'] = res['peer']['us_per_iteration'] / res['local']['us_per_iteration']
+    # reduced problem against the oracle (rank 0 runs the reference kmeans on the whole matrix)
+    n_small = min(n_img, 2) * (N_local // n_img)
+    Xs, ws = X[:n_small].contiguous(), w[:n_small].contiguous()
+    np.random.seed(1111)
+    init_s = dist_kmeans.distributed_init(ws.cpu().numpy(), K)
+    r = dist_kmeans.global_kmeans(Xs, ws, K, init_local=init_s, exchange='peer', comm=comm,
+                                  row0=rank * n_small)
+    gX = [torch.empty_like(Xs) for _ in range(world)]
+    gw = [torch.empty_like(ws) for _ in range(world)]
+    ga = [torch.empty_like(r.assign) for _ in range(world)]
+    gi = [torch.empty(n_small, dtype=torch.int32, device=dev) for _ in range(world)]
+    dist.all_gather(gX, Xs)
+    dist.all_gather(gw, ws)
+    dist.all_gather(ga, r.assign)
+    dist.all_gather(gi, torch.from_numpy(np.asarray(init_s, dtype=np.int32)).to(dev))
+    if rank == 0:
+        from oracle import spalign_oracle as so     # checker only
+        want, info = so.kmeans(K, torch.cat(gX).cpu().numpy().astype(np.float64),
+                               torch.cat(gw).cpu().numpy(),
+                               init_assign=torch.cat(gi).cpu().numpy().astype(np.float64),
+                               return_info=True, verbose=False)
+        got = torch.cat(ga).cpu().numpy()
+        res['check_vs_oracle'] = {
+            'rows': int(n_small) * world, 'identical_assignments': bool(np.array_equal(got, np.asarray(want).astype(np.int32))),
+            'iterations': [int(r.iters[0].item()), int(info['iters'])],
+            'status': [int(r.status[0].item()), int(info['status'])]}
+    dist.barrier()
+    comm.close()
+    return res
 
 
 def run_e2e(args, dev, labels, feats, world):
@@ -443,6 +560,7 @@ def main():
     ap.add_argument('--e2e-sub-batch', type=int, default=8, help='images per host->device sub-batch')
     ap.add_argument('--host-pool', type=int, default=16, help='distinct pinned host images')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-global-kmeans', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

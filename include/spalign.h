@@ -62,6 +62,7 @@ enum spalign_status {
 #define SPALIGN_KM_CONVERGED 0     /* all(new_assign == assign), batch_spalign_kmeans.py:158 */
 #define SPALIGN_KM_EMPTY_CLUSTER 1 /* "Terminate KMeans iteration due to ...", :173-181 */
 #define SPALIGN_KM_ITER_CAP 2      /* n_iter exhausted, :153 */
+#define SPALIGN_KM_COMM_TIMEOUT 3  /* multi-GPU only: a peer never delivered its partial sums */
 
 int spalign_abi_version(void);
 const char* spalign_last_error(void);
@@ -197,6 +198,10 @@ int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int pos_mode, 
  * centre; every update records how far each centre moved; a mode-2 sweep shifts the bounds by
  * that drift and only gathers, screens and re-bounds the rows whose bounds no longer prove that
  * the assignment is unchanged (fp32 rows, chunks of <= 1024 rows).  Results are identical. */
+/* counters: int32[n_chunks + G], zero on entry and on exit (tickets of the first-level reducers,
+ * indexed by chunk slot, then one per group).  The partials of a group are summed along a fixed
+ * tree -- runs of 32 consecutive slots in slot order, then the run sums in order -- by the chunks
+ * that finish last, so the serial tail of a group of n chunks reads n/32 + 32 vectors, not n. */
 int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
                            int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
                            const int64_t* chunks, int n_chunks, const int32_t* group_chunk_off,
@@ -230,6 +235,39 @@ int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,
                           double* centers, int32_t* iters, int32_t* status,
                           spalign_stream_t stream);
+
+/* ---- multi-GPU dataset-wide clustering (BASELINE configs[4]; build-defined: the reference has
+ * no collective on this path, direct_clustering.py:297-317 clusters one batch) -----------------
+ * Semantics: kmeans() of batch_spalign_kmeans.py:136-183 on the concatenation of all ranks'
+ * rows, rank r holding a contiguous slice.  One process per GPU.  A communicator owns one
+ * exchange buffer per rank (cudaMalloc), mapped into every peer process through CUDA IPC:
+ *   spalign_comm_create   allocate this rank's buffer for vectors of up to pv_cap doubles
+ *                         (pv = K*(D+2)+1); synchronises
+ *   spalign_comm_handle   64-byte IPC handle of the buffer (host memory); the caller gathers the
+ *                         handles of all ranks (torch.distributed / MPI / files)
+ *   spalign_comm_connect  map the peers' buffers; handles = world * 64 bytes, rank order (host)
+ * spalign_kmeans_iterate_dist = spalign_kmeans_iterate for G = 1 with the exchange inside the
+ * kernel: the CTA that finishes the local reduction stores this rank's K*(D+2)+1 sums into every
+ * rank's inbox over NVLink (plain stores + release flags at system scope), waits for the peers'
+ * flags and adds the world's vectors in rank order, so totals, centres and stop flags are
+ * bit-identical on all ranks and an iteration is ONE launch per GPU with no NCCL call and no host
+ * round trip.  Every rank must issue the same sequence of calls; launches after the stop
+ * condition exit at once (ranks may over-enqueue).  A peer that never answers (3 s) stops the
+ * group with SPALIGN_KM_COMM_TIMEOUT; the communicator is then unusable. */
+#define SPALIGN_COMM_HANDLE_BYTES 64
+typedef struct spalign_comm spalign_comm_t;
+int spalign_comm_create(int world, int rank, int64_t pv_cap, spalign_comm_t** out);
+int spalign_comm_handle(spalign_comm_t* comm, void* handle_out /* host, 64 bytes */);
+int spalign_comm_connect(spalign_comm_t* comm, const void* handles /* host, world*64 bytes */);
+int spalign_comm_destroy(spalign_comm_t* comm);
+int spalign_kmeans_iterate_dist(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                                int64_t pos_period, int64_t pos_row0, const double* w, int D,
+                                int K, const int64_t* chunks, int n_chunks,
+                                const int32_t* group_chunk_off, int mode, int n_iter,
+                                int32_t* assign, double* partials, double* totals,
+                                double* centers, int32_t* iters, int32_t* status,
+                                int32_t* counters, float* ub, float* lb, double* cdelta,
+                                spalign_comm_t* comm, spalign_stream_t stream);
 
 /* Diagnostics, synchronises the device: out_host[0] = rows screened in fp32 since the last
  * reset, out_host[1] = rows that needed the exact float64 pass (host int64[2]). */

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get('SPALIGN_LIB', os.path.join(_HERE, 'libspalign_b200.so
 I32, I64, U8 = 0, 1, 2
 F32, F64 = 0, 1
 F_LABEL_RANGE, F_NNZ_OVERFLOW, F_EMPTY_ROW = 1, 2, 4
-KM_RUNNING, KM_CONVERGED, KM_EMPTY_CLUSTER, KM_ITER_CAP = -1, 0, 1, 2
+KM_RUNNING, KM_CONVERGED, KM_EMPTY_CLUSTER, KM_ITER_CAP, KM_COMM_TIMEOUT = -1, 0, 1, 2, 3
+COMM_HANDLE_BYTES = 64
 ABI_VERSION = 1
 
 _p, _i, _l, _d, _z = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
@@ -42,6 +43,12 @@ SIGNATURES = {
                                   _p, _p]),
     'spalign_kmeans_iterate': (_i, [_p, _i, _l, _i, _i, _l, _l, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p,
                                     _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'spalign_kmeans_iterate_dist': (_i, [_p, _i, _l, _i, _i, _l, _l, _p, _i, _i, _p, _i, _p, _i, _i, _p,
+                                         _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'spalign_comm_create': (_i, [_i, _i, _l, C.POINTER(_p)]),
+    'spalign_comm_handle': (_i, [_p, _p]),
+    'spalign_comm_connect': (_i, [_p, _p]),
+    'spalign_comm_destroy': (_i, [_p]),
     'spalign_kmeans_finish': (_i, [_p, _i, _l, _i, _i, _l, _l, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _i, _i, _p]),
     'spalign_kmeans_reduce': (_i, [_p, _p, _i, _i, _i, _p, _p]),

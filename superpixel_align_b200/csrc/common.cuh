@@ -57,6 +57,20 @@ struct Carver {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Multi-GPU exchange state as the kernels see it (spalign_comm_* in comm.cu): every rank owns
+// an inbox [2][world][pv_cap] doubles and flags [2][world] in its own HBM, mapped into every
+// peer process (CUDA IPC, loads/stores travel over NVLink).
+constexpr int KM_MAX_WORLD = 8;
+struct PeerComm {
+  int world, rank;
+  long long pv_cap;
+  double* inbox[KM_MAX_WORLD];              // rank r's inbox as seen from this process
+  unsigned long long* flags[KM_MAX_WORLD];  // rank r's flags as seen from this process
+  unsigned long long* xcount;               // local: number of exchanges completed so far
+};
+// fills `out` for vectors of `pv` doubles (comm.cu)
+int comm_fill_peer(spalign_comm_t* comm, long long pv, PeerComm* out);
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 

@@ -25,6 +25,7 @@
 // persistent CTA per group, full sweeps; small problems), and the reduce / update kernels of
 // the three-step form that leaves room for an all-reduce.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -1378,6 +1379,44 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_groups_kernel(GroupAr
   }
 }
 
+// Reduction tree of the chunk partials of one group (the same in kmeans_reduce_kernel and in the
+// fused finish, so both give the same bits): runs of KM_SUPER consecutive slots are summed in
+// slot order, then the run sums are summed in run order.  In the fused finish the runs are
+// summed by different CTAs (the chunk of a run that finishes last), so the serial part of a
+// group of n chunks is n/KM_SUPER + KM_SUPER vector reads instead of n.
+constexpr int KM_SUPER = 32;
+
+// sum of base[i * stride], i = 0..n-1 ascending, U loads in flight (L2 loads: the values were
+// written by other CTAs of this launch)
+template <int U>
+__device__ __forceinline__ double ordered_sum_cg(const double* base, size_t stride, int n) {
+  double sum = 0.0;
+  int c = 0;
+  for (; c + U <= n; c += U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcg(base + (size_t)(c + u) * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) sum += v[u];
+  }
+  for (; c < n; ++c) sum += __ldcg(base + (size_t)c * stride);
+  return sum;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct SweepArgs {
   KmArgs a;
   const int64_t* chunks;  // [n_chunks][4]: group, row_begin, row_end, slot
@@ -1388,13 +1427,15 @@ struct SweepArgs {
   double* partials;       // [n_chunks][K*(D+2)+1]
   // fused finish (optional): the last chunk of a group to finish reduces and updates
   const int32_t* gco;     // [G+1] chunk offsets per group
-  int32_t* counters;      // [G] arrival tickets, zero between launches; NULL = no fused finish
+  int32_t* counters;      // [n_chunks + G] arrival tickets (first-level reducers by slot, then
+                          // groups), zero between launches; NULL = no fused finish
   double* totals;         // [G][K*(D+2)+1]
   double* centers_rw;     // [G][K][D]
   int32_t* iters;
   int32_t* status_rw;
   int n_iter;
   double* cdelta;         // [G][K] centre drift of the last update (Hamerly bounds); may be NULL
+  PeerComm peer;          // multi-GPU exchange of the reduced vector (world <= 1: none)
 };
 
 // centres / stop flags of one group from its reduced totals (shared by kmeans_update_kernel
@@ -1520,38 +1561,98 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_sweep_kernel(SweepArg
   }
   if (t == 0) out[pv - 1] = (double)*s.changed;
   if (g.counters != nullptr) {
-    // fused finish: the chunk that arrives last sums the group's partials in chunk order
-    // (same order as kmeans_reduce_kernel -> same bits) and applies the update
+    // fused finish: the chunks that arrive last sum the group's partials along the fixed tree
+    // (same as kmeans_reduce_kernel -> same bits) and apply the update
     __shared__ int s_last;
+    const int c0 = g.gco[grp], c1 = g.gco[grp + 1];
+    const int nch = c1 - c0;
+    const int nsup = (nch + KM_SUPER - 1) / KM_SUPER;
+    int32_t* gcount = g.counters + gridDim.x + grp;
     __threadfence();
     __syncthreads();
-    if (t == 0) {
-      const int nch = g.gco[grp + 1] - g.gco[grp];
-      s_last = atomicAdd(&g.counters[grp], 1) == nch - 1;
+    if (nsup > 1) {
+      // first level: the last chunk of this run of KM_SUPER slots sums the run into its first slot
+      const int sidx = (ck - c0) / KM_SUPER;
+      const int sb = c0 + sidx * KM_SUPER, se = min(sb + KM_SUPER, c1);
+      if (t == 0) s_last = atomicAdd(&g.counters[sb], 1) == se - sb - 1;
+      __syncthreads();
+      if (!s_last) return;
+      __threadfence();
+      double* run = g.partials + (size_t)sb * pv;
+      for (int j = t; j < (int)pv; j += 2 * KM_THREADS) {
+        const int j2 = j + KM_THREADS;
+        const double v0 = ordered_sum_cg<16>(run + j, pv, se - sb);
+        const double v1 = j2 < (int)pv ? ordered_sum_cg<16>(run + j2, pv, se - sb) : 0.0;
+        __stcg(run + j, v0);
+        if (j2 < (int)pv) __stcg(run + j2, v1);
+      }
+      if (t == 0) g.counters[sb] = 0;
+      __threadfence();
+      __syncthreads();
     }
+    if (t == 0) s_last = atomicAdd(gcount, 1) == (nsup > 1 ? nsup : nch) - 1;
     __syncthreads();
     if (s_last) {
       __threadfence();
       double* tt = g.totals + (size_t)grp * pv;
-      const int c0 = g.gco[grp], c1 = g.gco[grp + 1];
+      const double* first = g.partials + (size_t)c0 * pv;
+      const size_t stride = nsup > 1 ? (size_t)KM_SUPER * pv : pv;
+      const int terms = nsup > 1 ? nsup : nch;
+      const PeerComm& pc = g.peer;
+      unsigned long long seq = 0;
+      int par = 0;
+      if (pc.world > 1) {
+        seq = *pc.xcount + 1;
+        par = (int)(seq & 1ull);
+      }
       for (int j = t; j < (int)pv; j += KM_THREADS) {
-        double sum = 0.0;
-        int c = c0;
-        for (; c + 8 <= c1; c += 8) {  // 8 loads in flight, added in chunk order
-          double v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __ldcg(g.partials + (size_t)(c + u) * pv + j);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) sum += v[u];
+        const double sum = ordered_sum_cg<16>(first + j, stride, terms);
+        if (pc.world > 1) {
+          // publish this rank's vector into every rank's inbox (own one included)
+          const size_t slot = ((size_t)par * pc.world + pc.rank) * pc.pv_cap + j;
+          for (int r = 0; r < pc.world; ++r) pc.inbox[r][slot] = sum;
+        } else {
+          // mode 2: the partials are deltas of the running sums (rows that changed cluster)
+          tt[j] = (g.mode == 2 && j != (int)pv - 1) ? tt[j] + sum : sum;
         }
-        for (; c < c1; ++c) sum += __ldcg(g.partials + (size_t)c * pv + j);
-        // mode 2: the partials are deltas of the running sums (rows that changed cluster)
-        tt[j] = (g.mode == 2 && j != (int)pv - 1) ? tt[j] + sum : sum;
+      }
+      if (pc.world > 1) {
+        __shared__ int s_timeout;
+        if (t == 0) s_timeout = 0;
+        __threadfence_system();
+        __syncthreads();
+        if (t < pc.world) {
+          st_release_sys(pc.flags[t] + (size_t)par * pc.world + pc.rank, seq);
+          const unsigned long long* mine = pc.flags[pc.rank] + (size_t)par * pc.world + t;
+          const long long t0 = clock64();
+          while (ld_acquire_sys(mine) < seq) {
+            if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer is gone; give up cleanly
+              s_timeout = 1;
+              break;
+            }
+          }
+        }
+        __syncthreads();
+        if (s_timeout) {
+          if (t == 0) {
+            g.status_rw[grp] = SPALIGN_KM_COMM_TIMEOUT;
+            *gcount = 0;
+          }
+          return;
+        }
+        // every rank adds the world's vectors in rank order -> bit-identical totals everywhere
+        const double* in = pc.inbox[pc.rank] + (size_t)par * pc.world * pc.pv_cap;
+        for (int j = t; j < (int)pv; j += KM_THREADS) {
+          double sum = 0.0;
+          for (int r = 0; r < pc.world; ++r) sum += ld_volatile_f64(in + (size_t)r * pc.pv_cap + j);
+          tt[j] = (g.mode == 2 && j != (int)pv - 1) ? tt[j] + sum : sum;
+        }
+        if (t == 0) *pc.xcount = seq;
       }
       __syncthreads();
       km_update_group(tt, D, K, g.mode == 2 ? 1 : g.mode, g.n_iter,
                       g.centers_rw + (size_t)grp * K * D, g.iters, g.status_rw, grp, g.cdelta);
-      if (t == 0) g.counters[grp] = 0;
+      if (t == 0) *gcount = 0;
     }
   }
 }
@@ -1843,17 +1944,18 @@ kmeans_reduce_kernel(const double* __restrict__ partials, const int32_t* __restr
   const int grp = blockIdx.y;
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= pv) return;
+  // the tree of the fused finish: runs of KM_SUPER slots in order, then the run sums in order
+  const int c0 = gco[grp], c1 = gco[grp + 1];
+  const int nsup = (c1 - c0 + KM_SUPER - 1) / KM_SUPER;
   double sum = 0.0;
-  int c = gco[grp];
-  const int c1 = gco[grp + 1];
-  for (; c + 8 <= c1; c += 8) {  // 8 loads in flight, added in chunk order
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = partials[(size_t)(c + u) * pv + j];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) sum += v[u];
+  if (nsup <= 1) {
+    sum = ordered_sum_cg<16>(partials + (size_t)c0 * pv + j, pv, c1 - c0);
+  } else {
+    for (int s = 0; s < nsup; ++s) {
+      const int sb = c0 + s * KM_SUPER, se = min(sb + KM_SUPER, c1);
+      sum += ordered_sum_cg<16>(partials + (size_t)sb * pv + j, pv, se - sb);
+    }
   }
-  for (; c < c1; ++c) sum += partials[(size_t)c * pv + j];
   totals[(size_t)grp * pv + j] = sum;
 }
 
@@ -2116,20 +2218,19 @@ extern "C" int spalign_kmeans_sweep(const void* X, int x_dtype, int64_t ldx, int
   g.partials = partials;
   g.gco = nullptr; g.counters = nullptr; g.totals = nullptr; g.centers_rw = nullptr;
   g.iters = nullptr; g.status_rw = nullptr; g.n_iter = 0; g.cdelta = nullptr;
+  memset(&g.peer, 0, sizeof(g.peer));
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_sweep");
 }
 
-extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode,
-                                      int pos_w, int64_t pos_period, int64_t pos_row0,
-                                      const double* w, int D, int K, const int64_t* chunks,
-                                      int n_chunks, const int32_t* group_chunk_off, int mode,
-                                      int n_iter, int32_t* assign, double* partials,
-                                      double* totals, double* centers, int32_t* iters,
-                                      int32_t* status, int32_t* counters,
-                                      float* ub, float* lb, double* cdelta,
-                                      spalign_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+static int kmeans_iterate_impl(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
+                               int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
+                               const int64_t* chunks, int n_chunks,
+                               const int32_t* group_chunk_off, int mode, int n_iter,
+                               int32_t* assign, double* partials, double* totals, double* centers,
+                               int32_t* iters, int32_t* status, int32_t* counters, float* ub,
+                               float* lb, double* cdelta, void* comm, cudaStream_t stream) {
   SPALIGN_REQUIRE(chunks && group_chunk_off && assign && partials && totals && centers && iters &&
                       status && counters && n_chunks > 0 && mode >= 0 && mode <= 2,
                   "kmeans_iterate: bad arguments");
@@ -2149,8 +2250,44 @@ extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, i
   g.iters = iters; g.status_rw = status; g.n_iter = n_iter;
   g.cdelta = (ub && lb) ? cdelta : nullptr;
   g.a.ub = cdelta ? ub : nullptr; g.a.lb = cdelta ? lb : nullptr;
+  memset(&g.peer, 0, sizeof(g.peer));
+  if (comm != nullptr) {
+    rc = comm_fill_peer(static_cast<spalign_comm_t*>(comm), (long long)K * (D + 2) + 1, &g.peer);
+    if (rc) return rc;
+  }
   KM_DISPATCH(kmeans_sweep_kernel, g, n_chunks);
   return check_launch("kmeans_iterate");
+}
+
+extern "C" int spalign_kmeans_iterate(const void* X, int x_dtype, int64_t ldx, int pos_mode,
+                                      int pos_w, int64_t pos_period, int64_t pos_row0,
+                                      const double* w, int D, int K, const int64_t* chunks,
+                                      int n_chunks, const int32_t* group_chunk_off, int mode,
+                                      int n_iter, int32_t* assign, double* partials,
+                                      double* totals, double* centers, int32_t* iters,
+                                      int32_t* status, int32_t* counters,
+                                      float* ub, float* lb, double* cdelta,
+                                      spalign_stream_t stream_) {
+  return kmeans_iterate_impl(X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K,
+                             chunks, n_chunks, group_chunk_off, mode, n_iter, assign, partials,
+                             totals, centers, iters, status, counters, ub, lb, cdelta, nullptr,
+                             static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int spalign_kmeans_iterate_dist(const void* X, int x_dtype, int64_t ldx, int pos_mode,
+                                           int pos_w, int64_t pos_period, int64_t pos_row0,
+                                           const double* w, int D, int K, const int64_t* chunks,
+                                           int n_chunks, const int32_t* group_chunk_off, int mode,
+                                           int n_iter, int32_t* assign, double* partials,
+                                           double* totals, double* centers, int32_t* iters,
+                                           int32_t* status, int32_t* counters, float* ub,
+                                           float* lb, double* cdelta, spalign_comm_t* comm,
+                                           spalign_stream_t stream_) {
+  SPALIGN_REQUIRE(comm != nullptr, "kmeans_iterate_dist: NULL communicator");
+  return kmeans_iterate_impl(X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K,
+                             chunks, n_chunks, group_chunk_off, mode, n_iter, assign, partials,
+                             totals, centers, iters, status, counters, ub, lb, cdelta, comm,
+                             static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode,

@@ -403,7 +403,8 @@ class KMeansLarge:
 
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
-                 incremental=True, bounds=True, tail=True, tail_after=1, tail_slice=0):
+                 incremental=True, bounds=True, tail=True, tail_after=1, tail_slice=0,
+                 comm=None):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -415,6 +416,10 @@ class KMeansLarge:
         self.pos_period = pos_grid[0] * pos_grid[1] if pos_grid else 0
         self.pos_row0 = pos_row0
         self.allreduce = allreduce
+        self.comm = comm      # dist_kmeans.PeerComm: the exchange runs inside the iterate kernel
+        if comm is not None:
+            assert allreduce is None and fused and len(group_off_host) == 2, \
+                'peer-memory exchange: one global group, fused iterate kernel'
         self.chunks_per_group = chunks_per_group
         self.dev = dev = self.X.device
         self.w = w.to(torch.float64).contiguous()
@@ -428,7 +433,7 @@ class KMeansLarge:
         self.centers = torch.zeros((self.G, K, self.D), dtype=torch.float64, device=dev)
         self.iters = torch.zeros(self.G, dtype=torch.int32, device=dev)
         self.status = torch.full((self.G,), _lib.KM_RUNNING, dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(self.G, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(self.G + self.n_chunks, dtype=torch.int32, device=dev)
         self.ub = self.lb = self.cdelta = None
         if bounds and incremental and fused and self.code == _lib.F32:
             self.ub = torch.empty(self.N, dtype=torch.float32, device=dev)
@@ -441,7 +446,7 @@ class KMeansLarge:
         # the remaining iterations on its own (spalign_kmeans_finish), no per-iteration launch
         sizes = np.diff(self.goff)
         max_rows = int(sizes.max()) if self.G else 0
-        self.tail = (tail and self.ub is not None and allreduce is None and
+        self.tail = (tail and self.ub is not None and allreduce is None and comm is None and
                      chunks_per_group is None and
                      (max_rows <= self.TAIL_ROWS or
                       (max_rows <= 8 * self.TAIL_ROWS and self.G >= 148)))
@@ -468,9 +473,14 @@ class KMeansLarge:
             size_rank = np.zeros(len(rb), dtype=np.int64)
         else:
             # uniform chunks; per-CTA fixed cost (centres, screening set-up, partials) argues
-            # for large chunks, load balance for small ones: 32..256 rows by active volume
+            # for large chunks, load balance for small ones: 32..1024 rows by active volume
+            # (1024 = the limit of the bounds pass; large problems get large chunks and with
+            # them fewer partial-sum vectors for the fused reduction to add up)
+            # many small groups (per-image clustering) keep the 256-row cap tuned in round 1
             total = int(n.sum())
-            rpc = max(2 * self.TILE, min(16 * self.TILE, total // self.TARGET_CHUNKS))
+            cap = int(os.environ.get('SPALIGN_KM_CHUNK_ROWS', 0)) or \
+                (64 * self.TILE if int(n.max()) > 4096 else 16 * self.TILE)
+            rpc = max(2 * self.TILE, min(cap, total // self.TARGET_CHUNKS))
             rpc = -(-rpc // self.TILE) * self.TILE
             per = np.full(len(active), rpc, dtype=np.int64)
             nch = np.maximum(1, -(-n // per))
@@ -491,6 +501,7 @@ class KMeansLarge:
         self.n_chunks = tot
         if getattr(self, 'partials', None) is not None and tot > self.partials.shape[0]:
             self.partials = torch.zeros((tot, self.pv), dtype=torch.float64, device=self.dev)
+            self.counters = torch.zeros(self.G + tot, dtype=torch.int32, device=self.dev)
         self.chunks = torch.from_numpy(chunks).to(self.dev, non_blocking=True)
         self.gco = torch.from_numpy(gco).to(self.dev, non_blocking=True)
 
@@ -505,13 +516,17 @@ class KMeansLarge:
                 if self._full_done:
                     mode = 2
                 self._full_done = True
-            check(self._lib.spalign_kmeans_iterate(
-                _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
-                self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
-                self.n_chunks, _ptr(self.gco), mode, self.n_iter, _ptr(self.assign),
-                _ptr(self.partials), _ptr(self.totals), _ptr(self.centers), _ptr(self.iters),
-                _ptr(self.status), _ptr(self.counters), _ptr(self.ub),
-                _ptr(self.lb), _ptr(self.cdelta), _stream()), 'kmeans_iterate')
+            args = (_ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
+                    self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K, _ptr(self.chunks),
+                    self.n_chunks, _ptr(self.gco), mode, self.n_iter, _ptr(self.assign),
+                    _ptr(self.partials), _ptr(self.totals), _ptr(self.centers), _ptr(self.iters),
+                    _ptr(self.status), _ptr(self.counters), _ptr(self.ub),
+                    _ptr(self.lb), _ptr(self.cdelta))
+            if self.comm is not None:
+                check(self._lib.spalign_kmeans_iterate_dist(*args, self.comm.handle, _stream()),
+                      'kmeans_iterate_dist')
+            else:
+                check(self._lib.spalign_kmeans_iterate(*args, _stream()), 'kmeans_iterate')
             _count('kmeans_sweep')
             return
         check(self._lib.spalign_kmeans_sweep(

@@ -504,6 +504,31 @@ def test_kmeans_fused_iterate_equals_three_kernel_path(ops):
         assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
 
 
+def test_kmeans_two_level_reduction_tree(ops):
+    # groups cut into more than 32 chunks: the partial sums are added along the two-level tree
+    # (runs of 32 slots by the chunk of the run that finishes last, then the run sums); the
+    # fused kernel, the three-call form and the running-sum mode must agree with the oracle
+    rs = np.random.RandomState(4)
+    sizes = [9000, 700, 5300]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = _blobs(rs, off[-1], 34, 4, spread=1.5)
+    w = rs.uniform(0, 1, len(X))
+    init = np.concatenate([so.kmeans_init(4, w[a:b], rng=rs) for a, b in zip(off[:-1], off[1:])]).astype(np.int32)
+    args = (torch.from_numpy(X).to(dev()), torch.from_numpy(w).to(dev()), torch.from_numpy(init).to(dev()), 4, off)
+    a = ops.KMeansLarge(*args, chunks_per_group=150, incremental=False).run()
+    assert a is not None and (np.diff(ops.KMeansLarge(*args, chunks_per_group=150).gco.cpu().numpy()) > 64).any()
+    b = ops.KMeansLarge(*args, chunks_per_group=150, fused=False).run(poll=3)
+    assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
+    assert torch.equal(a.status, b.status) and torch.equal(a.centers, b.centers)   # bit-identical
+    c = ops.KMeansLarge(*args, chunks_per_group=150).run()                          # running sums + bounds
+    assert torch.equal(a.assign, c.assign) and torch.equal(a.iters, c.iters) and torch.equal(a.status, c.status)
+    for g, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        want, info = so.kmeans(4, X[lo:hi].astype(np.float64), w[lo:hi], init_assign=init[lo:hi].astype(np.float64),
+                               return_info=True, verbose=False)
+        assert np.array_equal(a.assign[lo:hi].cpu().numpy(), np.asarray(want).astype(np.int32))
+        assert a.iters[g].item() == info['iters'] and a.status[g].item() == info['status']
+
+
 @pytest.mark.parametrize('sizes,tail_rows', [([900, 1000, 64, 1700, 1], 2048), ([2500, 3100, 1025], 4096)])
 def test_kmeans_finish_kernel_equals_per_iteration_launches(ops, sizes, tail_rows, monkeypatch):
     # one persistent CTA per group (spalign_kmeans_finish; groups above 1024 rows loop over

@@ -1,5 +1,7 @@
 """Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): dataset-wide k-means over row
-shards with the NCCL all-reduce of the totals buffer, against the single-process oracle."""
+shards (BASELINE configs[4]) against the single-process oracle, with the exchange inside the
+iterate kernel over peer-mapped memory (NVLink) and with the NCCL all-reduce of the totals
+buffer between reduce and update."""
 import os
 import socket
 
@@ -10,6 +12,12 @@ torch = pytest.importorskip('torch')
 
 pytestmark = pytest.mark.gpu
 
+CASES = {
+    # name: (N, D, K, centroid columns?)
+    'descriptors': (6000, 514, 4, True),       # a handful of chunks per rank: one-level reduction
+    'many_chunks': (60000, 18, 5, False),      # > 32 chunks per rank: two-level reduction tree
+}
+
 
 def _free_port():
     s = socket.socket()
@@ -19,7 +27,20 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _problem(name):
+    N, D, K, pos = CASES[name]
+    rs = np.random.RandomState(0)
+    cent = rs.standard_normal((K, D)) * 4
+    X = (cent[rs.randint(0, K, N)] + rs.standard_normal((N, D))).astype(np.float32)
+    if pos:
+        X[:, -2] = rs.uniform(0, 1023, N)
+        X[:, -1] = rs.uniform(0, 2047, N)
+    w = rs.uniform(0, 1, N)
+    return X, w, K
+
+
+def _worker(rank, world, port, q, exchange, case):
+    import time
     import torch.distributed as dist
     from oracle import spalign_oracle as so
     from superpixel_align_b200 import dist_kmeans, shard
@@ -28,39 +49,56 @@ def _worker(rank, world, port, q):
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
-        rs = np.random.RandomState(0)
-        N, D, K = 6000, 514, 4
-        cent = rs.standard_normal((K, D)) * 4
-        X = (cent[rs.randint(0, K, N)] + rs.standard_normal((N, D))).astype(np.float32)
-        X[:, -2] = rs.uniform(0, 1023, N)
-        X[:, -1] = rs.uniform(0, 2047, N)
-        w = rs.uniform(0, 1, N)
-        lo, hi = shard.shard_range(N, world, rank)
-        np.random.seed(1111)
-        res = dist_kmeans.global_kmeans(torch.from_numpy(X[lo:hi]).to(dev),
-                                        torch.from_numpy(w[lo:hi]).to(dev), K)
+        X, w, K = _problem(case)
+        lo, hi = shard.shard_range(len(X), world, rank)
+        Xd, wd = torch.from_numpy(X[lo:hi]).to(dev), torch.from_numpy(w[lo:hi]).to(dev)
+        msgs = []
+        for rep in range(2):           # second run: warm, timed
+            np.random.seed(1111)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.time()
+            res = dist_kmeans.global_kmeans(Xd, wd, K, exchange=exchange)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
         np.random.seed(1111)
         want, info = so.kmeans(K, X.astype(np.float64), w, return_info=True, verbose=False)
         got = res.assign.cpu().numpy()
         ok = np.array_equal(got, np.asarray(want)[lo:hi].astype(np.int32)) and \
             res.iters[0].item() == info['iters'] and res.status[0].item() == info['status']
-        q.put((rank, 'ok' if ok else 'mismatch iters %d vs %d' % (res.iters[0].item(), info['iters'])))
+        # centres are replicated: bit-identical on every rank
+        cen = res.centers.clone()
+        ref = cen.clone()
+        dist.broadcast(ref, 0)
+        ok = ok and torch.equal(cen, ref)
+        msgs.append('%s/%s world %d: %d iterations, %.1f ms wall incl. init' %
+                    (case, exchange, world, info['iters'], dt * 1e3))
+        q.put((rank, 'ok' if ok else 'mismatch iters %d vs %d' % (res.iters[0].item(), info['iters']),
+               msgs))
     except Exception as e:  # pragma: no cover
-        q.put((rank, repr(e)))
+        q.put((rank, repr(e), []))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_global_kmeans_two_gpus_matches_oracle():
+@pytest.mark.parametrize('case', sorted(CASES))
+@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_global_kmeans_matches_oracle(world, exchange, case):
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, exchange, case))
+             for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in procs)
+    got = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(60)
-    assert res == {0: 'ok', 1: 'ok'}, res
+    for _, _, msgs in got:
+        for m in msgs[:1]:
+            print(m)
+    assert {r: s for r, s, _ in got} == {r: 'ok' for r in range(world)}, got
