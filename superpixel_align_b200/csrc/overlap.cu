@@ -15,6 +15,8 @@
 //
 // The only floating-point reduction (prior) is summed in sorted column order with a fixed
 // tree, so the whole result is bit-reproducible.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace spalign {
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(256)
 scan_finish_kernel(const int* __restrict__ row_nnz, int64_t R, const int* __restrict__ tile_sum,
                    int n_tiles, int* indptr, int64_t* nnz_flags, int64_t nnz_cap,
                    int* heavy_rows, int* heavy_count, int heavy_cap,
-                   const int* __restrict__ pair_count, int n_img) {
+                   const int* __restrict__ pair_count, int n_img, int heavy_thr) {
   if (blockIdx.x == 0) {  // high-water mark of pairs per image (sizes nnz_cap after an overflow)
     int mx = 0;
     for (int i = threadIdx.x; i < n_img; i += 256) mx = max(mx, pair_count[i]);
@@ -517,7 +519,7 @@ scan_finish_kernel(const int* __restrict__ row_nnz, int64_t R, const int* __rest
     int64_t idx = base + k;
     if (idx < R) {
       indptr[idx] = (int)run;
-      if (vals[k] > WARP_TIER_MAX) {
+      if (vals[k] > heavy_thr) {
         int h = atomicAdd(heavy_count, 1);
         if (h < heavy_cap) heavy_rows[h] = (int)idx;
       }
@@ -737,6 +739,501 @@ rowsort_heavy_kernel(OverlapWs ws, const int* __restrict__ indptr, int ncell, in
   }
 }
 
+// ==========================================================================================
+// Stride-8 pipeline (DRN stride 8: 8x8-pixel cells), the path of every BASELINE config:
+//
+//   init_s8     zero the row cursors; prior lookup tables (sums of gx over every 4-bit column
+//               subset of each half cell, per cell column; sums of gy / gx per cell)
+//   emit_s8     one thread per cell, blocks of 16 x 8 cells.  The 64 labels sit in registers;
+//               per distinct label one pass of 64 compares builds the pixel mask (the first
+//               pass doubles as the uniformity test: ~70 % of the cells stop there with closed
+//               forms).  count, sum of row / column offsets (popcounts) are PACKED into one
+//               word, the prior comes from the nibble tables (8 rows x 2 lookups) or, for the
+//               last label of a cell, as the complement of the whole-cell prior.  The pair goes
+//               straight into the row's BUCKET (128 slots of 16 bytes; slot = one returning
+//               atomic on the row cursor, which is also the row length); rows longer than a
+//               bucket spill into a global list.  No other atomics: area and the centroid sums
+//               are rebuilt exactly from the packed words by rowsort.
+//   scan        cursors -> indptr (shared with the generic pipeline), rows > 128 cells listed
+//   spill       spilled pairs -> the tail of their row segment (only rows > 128 cells)
+//   rowsort     one warp per row: bitonic sort by cell id straight out of the bucket, unpack,
+//               integer sums (area, sum_y, sum_x) and the float64 prior in sorted order
+//   heavy       rows > 128 cells: dense scatter + ordered compaction
+// ==========================================================================================
+constexpr int BUCKET_CAP = 128;
+constexpr int TILE_W = 16, TILE_H = 8;  // cells per emit block
+#ifndef EMIT2_MIN_BLOCKS
+#define EMIT2_MIN_BLOCKS 4
+#endif
+
+struct S8Ws {
+  int* zero_begin;
+  size_t zero_ints;
+  int* cursor;       // [R] pairs of the row so far (= row length after emit)
+  int* cursor2;      // [R] spilled pairs placed so far
+  int* heavy_count;  // [1]
+  int* spill_count;  // [1]
+  int* tile_sum;
+  int* heavy_rows;
+  int heavy_cap;
+  int4* bucket;      // [R][BUCKET_CAP]: (cell, packed, prior lo, prior hi)
+  int* t_row;        // spill list [cap]
+  int* t_col;
+  int* t_cnt;
+  double* t_prior;
+  int* u_col;        // [cap] tails of heavy rows at their CSR position; u_prior doubles as the
+  int* u_cnt;        //       sorted-prior scratch of 65..128-cell rows
+  double* u_prior;
+  int* d_cnt;        // [HEAVY_SLOTS * ncell]
+  double* d_prior;
+  double* gxT;       // [fw][32]
+  double* gx8;       // [fw]
+  double* gy8;       // [fh]
+};
+
+size_t carve_s8(S8Ws& ws, void* base, int fh, int fw, int64_t R, int64_t cap) {
+  Carver c(base);
+  const int ncell = fh * fw;
+  int n_tiles = (int)((R + SCAN_TILE - 1) / SCAN_TILE);
+  ws.heavy_cap = (int)(cap / (BUCKET_CAP + 1) + 1);
+  ws.cursor = c.take<int>(R);
+  ws.zero_begin = ws.cursor;
+  ws.cursor2 = c.take<int>(R);
+  ws.heavy_count = c.take<int>(1);
+  ws.spill_count = c.take<int>(1);
+  ws.zero_ints = c.off / sizeof(int);
+  ws.tile_sum = c.take<int>(n_tiles);
+  ws.heavy_rows = c.take<int>(ws.heavy_cap);
+  ws.bucket = c.take<int4>((size_t)R * BUCKET_CAP);
+  ws.t_row = c.take<int>(cap);
+  ws.t_col = c.take<int>(cap);
+  ws.t_cnt = c.take<int>(cap);
+  ws.t_prior = c.take<double>(cap);
+  ws.u_col = c.take<int>(cap);
+  ws.u_cnt = c.take<int>(cap);
+  ws.u_prior = c.take<double>(cap);
+  ws.d_cnt = c.take<int>((size_t)HEAVY_SLOTS * ncell);
+  ws.d_prior = c.take<double>((size_t)HEAVY_SLOTS * ncell);
+  ws.gxT = c.take<double>((size_t)fw * 32);
+  ws.gx8 = c.take<double>(fw);
+  ws.gy8 = c.take<double>(fh);
+  return c.used();
+}
+
+// packed pair word: count (7 bits, 1..64) | sum of row offsets (8 bits, <= 224) << 7 |
+// sum of column offsets (8 bits) << 15
+constexpr int PACKED_FULL = 64 | (224 << 7) | (224 << 15);
+__device__ __forceinline__ int packed_cnt(int p) { return p & 127; }
+__device__ __forceinline__ int packed_sy(int p) { return (p >> 7) & 255; }
+__device__ __forceinline__ int packed_sx(int p) { return (p >> 15) & 255; }
+
+__global__ void init_s8_kernel(S8Ws ws, int fh, int fw, const double* __restrict__ gy,
+                               const double* __restrict__ gx, int64_t* nnz_flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < ws.zero_ints; k += stride) ws.zero_begin[k] = 0;
+  if (i < 4) nnz_flags[i] = 0;
+  if (gy == nullptr) return;
+  for (size_t k = i; k < (size_t)fw * 32; k += stride) {
+    const int c = (int)(k >> 5), n = (int)(k & 15), half = (int)((k >> 4) & 1);
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((n >> j) & 1) sum = __dadd_rn(sum, gx[c * 8 + half * 4 + j]);
+    ws.gxT[k] = sum;
+  }
+  for (size_t k = i; k < (size_t)fw; k += stride) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum = __dadd_rn(sum, gx[k * 8 + j]);
+    ws.gx8[k] = sum;
+  }
+  for (size_t k = i; k < (size_t)fh; k += stride) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum = __dadd_rn(sum, gy[k * 8 + j]);
+    ws.gy8[k] = sum;
+  }
+}
+
+__device__ __forceinline__ void store_pair(const S8Ws& ws, int row, int pos, const int4& e,
+                                           int64_t spill_cap, int64_t* nnz_flags) {
+  if (pos < BUCKET_CAP) {
+    ws.bucket[(size_t)row * BUCKET_CAP + pos] = e;
+  } else {
+    const int sp = atomicAdd(ws.spill_count, 1);
+    if (sp < spill_cap) {
+      ws.t_row[sp] = row;
+      ws.t_col[sp] = e.x;
+      ws.t_cnt[sp] = e.y;
+      ws.t_prior[sp] = __hiloint2double(e.w, e.z);
+    } else {
+      atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+               (unsigned long long)SPALIGN_F_NNZ_OVERFLOW);
+    }
+  }
+}
+__device__ __forceinline__ void place_pair(const S8Ws& ws, int row, const int4& e,
+                                           int64_t spill_cap, int64_t* nnz_flags) {
+  store_pair(ws, row, atomicAdd(&ws.cursor[row], 1), e, spill_cap, nnz_flags);
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(TILE_W * TILE_H, EMIT2_MIN_BLOCKS)
+emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
+                 const int64_t* __restrict__ sp_off, const double* __restrict__ gy, S8Ws ws,
+                 int64_t spill_cap, int64_t* nnz_flags) {
+  // pairs of this thread's cell wait here until all of them are known, then their slot atomics
+  // are issued back to back (one exposed round trip per cell instead of one per label)
+  constexpr int PEND = 4;
+  __shared__ int4 s_pend[PEND][TILE_W * TILE_H];
+  __shared__ int s_prow[PEND][TILE_W * TILE_H];
+  const int t = threadIdx.x, tx = t & (TILE_W - 1), ty = t / TILE_W;
+  const int img = blockIdx.z;
+  const int cx = blockIdx.x * TILE_W + tx, cy = blockIdx.y * TILE_H + ty;
+  const bool have_prior = gy != nullptr;
+  if (cx >= fw || cy >= fh) return;
+  const int c = cy * fw + cx;
+  const LabelT* p = labels + ((size_t)img * H + (size_t)cy * 8) * W + (size_t)cx * 8;
+  int v[64];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (sizeof(LabelT) == 4) {
+      // (L1-allocating loads: mixed cells re-read single pixels below)
+      const int4 a = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
+      const int4 b = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + 1);
+      v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
+      v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
+    }
+  }
+  const int64_t row0 = sp_off[img];
+  const int n_sp = (int)(sp_off[img + 1] - row0);
+  if (sizeof(LabelT) == 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        longlong2 a = __ldg(q + h);
+        v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;
+        v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+      }
+    }
+  }
+  const double* gxT = ws.gxT + (size_t)cx * 32;
+  const double cell_prior = have_prior ? __dmul_rn(ws.gy8[cy], ws.gx8[cx]) : 0.0;
+  unsigned long long remaining = ~0ull;
+  double emitted_prior = 0.0;
+  bool can_complement = true, bad = false;
+  int npend = 0;
+  int L = v[0];
+  while (true) {
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (v[j] == L) lo |= 1u << j;
+      if (v[32 + j] == L) hi |= 1u << j;
+    }
+    const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    remaining &= ~m;
+    // next label: the first pixel not covered yet (re-read, L1 hit; issued before the work on
+    // the current label so that its latency hides behind it)
+    LabelT nextq = 0;
+    if (remaining != 0ull) {
+      const int i = __ffsll((long long)remaining) - 1;
+      nextq = __ldg(p + (size_t)(i >> 3) * W + (i & 7));
+    }
+    if ((unsigned)L < (unsigned)n_sp) {
+      const int cnt = __popc(lo) + __popc(hi);
+      int packed = PACKED_FULL;
+      double pr = cell_prior;
+      if (cnt != 64) {
+        // bit i = pixel row i >> 3, column i & 7: sums of the offsets of the set bits
+        const int sxl = __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) +
+                        4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull);
+        const int syl = __popcll(m & 0xff00ff00ff00ff00ull) + 2 * __popcll(m & 0xffff0000ffff0000ull) +
+                        4 * __popcll(m & 0xffffffff00000000ull);
+        packed = cnt | (syl << 7) | (sxl << 15);
+        if (have_prior) {
+          if (remaining == 0ull && can_complement) {
+            // last label of the cell: whole-cell prior minus what the other labels took
+            pr = __dadd_rn(cell_prior, -emitted_prior);
+          } else {
+            pr = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
+              const double rs = __dadd_rn(__ldg(gxT + (b & 15u)), __ldg(gxT + 16 + (b >> 4)));
+              pr = __fma_rn(__ldg(gy + cy * 8 + r), rs, pr);
+            }
+            emitted_prior = __dadd_rn(emitted_prior, pr);
+          }
+        }
+      }
+      if (npend == PEND) {  // more than PEND labels in one cell: place the oldest now
+        const int row = s_prow[0][t];
+        const int4 e = s_pend[0][t];
+#pragma unroll
+        for (int k = 0; k + 1 < PEND; ++k) {
+          s_prow[k][t] = s_prow[k + 1][t];
+          s_pend[k][t] = s_pend[k + 1][t];
+        }
+        --npend;
+        place_pair(ws, row, e, spill_cap, nnz_flags);
+      }
+      s_prow[npend][t] = (int)(row0 + L);
+      s_pend[npend][t] = make_int4(c, packed, __double2loint(pr), __double2hiint(pr));
+      ++npend;
+    } else {  // label outside [0, n_sp): flag it, emit nothing
+      bad = true;
+      can_complement = false;
+    }
+    if (remaining == 0ull) break;
+    L = (sizeof(LabelT) == 4) ? (int)nextq
+                              : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
+  }
+  // slot atomics of all pairs of the cell, back to back, then the 16-byte bucket stores
+  int pos[PEND];
+#pragma unroll
+  for (int k = 0; k < PEND; ++k)
+    if (k < npend) pos[k] = atomicAdd(&ws.cursor[s_prow[k][t]], 1);
+#pragma unroll
+  for (int k = 0; k < PEND; ++k)
+    if (k < npend) store_pair(ws, s_prow[k][t], pos[k], s_pend[k][t], spill_cap, nnz_flags);
+  if (bad)
+    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+             (unsigned long long)SPALIGN_F_LABEL_RANGE);
+}
+
+// spilled pairs (rows longer than a bucket) -> tail of their row segment
+__global__ void __launch_bounds__(256)
+spill_scatter_kernel(S8Ws ws, const int* __restrict__ indptr, int64_t nnz_cap,
+                     const int64_t* __restrict__ nnz_flags) {
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
+  const int n = *ws.spill_count;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < n; t += gridDim.x * 256) {
+    const int r = ws.t_row[t];
+    const int64_t pos = (int64_t)indptr[r] + BUCKET_CAP + atomicAdd(&ws.cursor2[r], 1);
+    if (pos < nnz_cap) {
+      ws.u_col[pos] = ws.t_col[t];
+      ws.u_cnt[pos] = ws.t_cnt[t];
+      ws.u_prior[pos] = ws.t_prior[t];
+    }
+  }
+}
+
+__device__ __forceinline__ double int4_prior(const int4& e) {
+  return __hiloint2double(e.w, e.z);
+}
+
+// one warp per row of <= BUCKET_CAP cells, straight out of the bucket
+__global__ void __launch_bounds__(256)
+rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int* counts,
+                      int* area, int64_t* sum_y, int64_t* sum_x, double* sum_prior,
+                      const int64_t* __restrict__ nnz_flags, int ncell) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
+  if (r >= R) return;
+  const int lane = lane_id();
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) {
+    // capacity exceeded: leave an EMPTY matrix behind (no row reaches into unwritten storage),
+    // the flag tells the caller
+    if (lane == 0) {
+      indptr[r] = 0;
+      if (r == R - 1) indptr[R] = 0;
+      area[r] = 0;
+      sum_y[r] = 0;
+      sum_x[r] = 0;
+      if (sum_prior != nullptr) sum_prior[r] = 0.0;
+    }
+    return;
+  }
+  const int L = ws.cursor[r];
+  if (L > BUCKET_CAP) return;
+  const int base = indptr[r];
+  const int4* bk = ws.bucket + (size_t)r * BUCKET_CAP;
+  int a_sum = 0;
+  long long y_sum = 0, x_sum = 0;
+  double ps = 0.0;
+  if (L <= 64 && ncell <= (1 << 24)) {
+    // bitonic sort of (cell << 7 | slot) keys, two per lane (elements lane and lane + 32)
+    const unsigned PAD = 0xffffffffu;
+    unsigned k0 = lane < L ? ((unsigned)bk[lane].x << 7) | (unsigned)lane : PAD;
+    unsigned k1 = lane + 32 < L ? ((unsigned)bk[lane + 32].x << 7) | (unsigned)(lane + 32) : PAD;
+    if (L > 32) {
+#pragma unroll
+      for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          if (j == 32) {
+            const unsigned mn = min(k0, k1), mx = max(k0, k1);
+            k0 = mn;
+            k1 = mx;
+          } else {
+            const unsigned p0 = __shfl_xor_sync(0xffffffffu, k0, j);
+            const unsigned p1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            const bool lower = (lane & j) == 0;
+            const bool up0 = (lane & k) == 0, up1 = ((lane + 32) & k) == 0;
+            k0 = (lower == up0) ? min(k0, p0) : max(k0, p0);
+            k1 = (lower == up1) ? min(k1, p1) : max(k1, p1);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned p0 = __shfl_xor_sync(0xffffffffu, k0, j);
+          const bool lower = (lane & j) == 0, up0 = (lane & k) == 0 || k == 32;
+          k0 = (lower == up0) ? min(k0, p0) : max(k0, p0);
+        }
+      }
+    }
+    double pv1 = 0.0;
+    if (lane < L) {
+      const int4 e = bk[k0 & 127u];
+      const int cn = packed_cnt(e.y), cyy = e.x / fw, cxx = e.x - cyy * fw;
+      indices[base + lane] = e.x;
+      counts[base + lane] = cn;
+      a_sum = cn;
+      y_sum = (long long)cn * (cyy * 8) + packed_sy(e.y);
+      x_sum = (long long)cn * (cxx * 8) + packed_sx(e.y);
+      ps = __dadd_rn(0.0, int4_prior(e));
+    }
+    if (lane + 32 < L) {
+      const int4 e = bk[k1 & 127u];
+      const int cn = packed_cnt(e.y), cyy = e.x / fw, cxx = e.x - cyy * fw;
+      indices[base + lane + 32] = e.x;
+      counts[base + lane + 32] = cn;
+      a_sum += cn;
+      y_sum += (long long)cn * (cyy * 8) + packed_sy(e.y);
+      x_sum += (long long)cn * (cxx * 8) + packed_sx(e.y);
+      pv1 = int4_prior(e);
+      ps = __dadd_rn(ps, pv1);
+    }
+  } else {
+    double* sorted_prior = ws.u_prior;  // this row's CSR range is unused by the heavy tier
+    for (int a = 0; a < L; a += 32) {
+      const int e = a + lane;
+      const bool valid = e < L;
+      const int4 me = valid ? bk[e] : make_int4(0x7fffffff, 0, 0, 0);
+      int rank = 0;
+      for (int b = 0; b < L; b += 32) {
+        const int oc = (b + lane < L) ? bk[b + lane].x : 0x7fffffff;
+        const int nb = min(32, L - b);
+        for (int j = 0; j < nb; ++j) {
+          const int o = __shfl_sync(0xffffffffu, oc, j);
+          rank += (o < me.x) ? 1 : 0;
+        }
+      }
+      if (valid) {
+        const int cn = packed_cnt(me.y), cyy = me.x / fw, cxx = me.x - cyy * fw;
+        indices[base + rank] = me.x;
+        counts[base + rank] = cn;
+        sorted_prior[base + rank] = int4_prior(me);
+        a_sum += cn;
+        y_sum += (long long)cn * (cyy * 8) + packed_sy(me.y);
+        x_sum += (long long)cn * (cxx * 8) + packed_sx(me.y);
+      }
+    }
+    if (sum_prior != nullptr) {
+      __syncwarp();
+      for (int e = lane; e < L; e += 32) ps = __dadd_rn(ps, sorted_prior[base + e]);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
+    y_sum += __shfl_xor_sync(0xffffffffu, y_sum, d);
+    x_sum += __shfl_xor_sync(0xffffffffu, x_sum, d);
+    ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, d));
+  }
+  if (lane == 0) {
+    area[r] = a_sum;
+    sum_y[r] = y_sum;
+    sum_x[r] = x_sum;
+    if (sum_prior != nullptr) sum_prior[r] = ps;
+  }
+}
+
+// rows longer than a bucket: bucket + spilled tail -> dense per-cell array -> ordered compaction
+__global__ void __launch_bounds__(HEAVY_THREADS)
+rowsort_heavy_s8_kernel(S8Ws ws, const int* __restrict__ indptr, int ncell, int fw, int* indices,
+                        int* counts, int* area, int64_t* sum_y, int64_t* sum_x,
+                        double* sum_prior, const int64_t* __restrict__ nnz_flags) {
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
+  const int n_heavy = min(*ws.heavy_count, ws.heavy_cap);
+  int* d_cnt = ws.d_cnt + (size_t)blockIdx.x * ncell;
+  double* d_prior = ws.d_prior + (size_t)blockIdx.x * ncell;
+  __shared__ double red_p[HEAVY_THREADS];
+  __shared__ int red_a[HEAVY_THREADS];
+  __shared__ long long red_y[HEAVY_THREADS];
+  __shared__ long long red_x[HEAVY_THREADS];
+  for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const int r = ws.heavy_rows[h];
+    const int base = indptr[r];
+    const int L = indptr[r + 1] - base;
+    const int4* bk = ws.bucket + (size_t)r * BUCKET_CAP;
+    for (int c = threadIdx.x; c < ncell; c += HEAVY_THREADS) d_cnt[c] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < L; e += HEAVY_THREADS) {
+      int c, pk;
+      double pv;
+      if (e < BUCKET_CAP) {
+        const int4 q = bk[e];
+        c = q.x; pk = q.y; pv = int4_prior(q);
+      } else {
+        c = ws.u_col[base + e]; pk = ws.u_cnt[base + e]; pv = ws.u_prior[base + e];
+      }
+      d_cnt[c] = pk;
+      d_prior[c] = pv;
+    }
+    __syncthreads();
+    int running = 0;
+    int a_sum = 0;
+    long long y_sum = 0, x_sum = 0;
+    double p_sum = 0.0;
+    for (int c0 = 0; c0 < ncell; c0 += HEAVY_THREADS) {
+      const int c = c0 + threadIdx.x;
+      const int pk = c < ncell ? d_cnt[c] : 0;
+      const int flag = pk != 0 ? 1 : 0;
+      int total;
+      const int excl = block_excl_scan_256(flag, &total);
+      if (flag) {
+        const int cn = packed_cnt(pk), cyy = c / fw, cxx = c - cyy * fw;
+        indices[base + running + excl] = c;
+        counts[base + running + excl] = cn;
+        a_sum += cn;
+        y_sum += (long long)cn * (cyy * 8) + packed_sy(pk);
+        x_sum += (long long)cn * (cxx * 8) + packed_sx(pk);
+        p_sum = __dadd_rn(p_sum, d_prior[c]);
+      }
+      running += total;
+    }
+    red_p[threadIdx.x] = p_sum;
+    red_a[threadIdx.x] = a_sum;
+    red_y[threadIdx.x] = y_sum;
+    red_x[threadIdx.x] = x_sum;
+    __syncthreads();
+    for (int s = HEAVY_THREADS / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        red_p[threadIdx.x] = __dadd_rn(red_p[threadIdx.x], red_p[threadIdx.x + s]);
+        red_a[threadIdx.x] += red_a[threadIdx.x + s];
+        red_y[threadIdx.x] += red_y[threadIdx.x + s];
+        red_x[threadIdx.x] += red_x[threadIdx.x + s];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      area[r] = red_a[0];
+      sum_y[r] = red_y[0];
+      sum_x[r] = red_x[0];
+      if (sum_prior != nullptr) sum_prior[r] = red_p[0];
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename LabelT>
 __global__ void __launch_bounds__(256)
@@ -785,10 +1282,14 @@ extern "C" int spalign_label_max(const void* labels, int label_dtype, int n_img,
 
 extern "C" size_t spalign_overlap_workspace_bytes(int n_img, int H, int W, int fh, int fw,
                                                   int64_t n_rows, int64_t nnz_cap) {
-  (void)H;
-  (void)W;
   OverlapWs ws;
-  return carve(ws, nullptr, n_img, fh * fw, n_rows, nnz_cap) + 256;
+  size_t need = carve(ws, nullptr, n_img, fh * fw, n_rows, nnz_cap) + 256;
+  if (H == 8 * fh && W == 8 * fw) {
+    S8Ws w8;
+    const size_t need8 = carve_s8(w8, nullptr, fh, fw, n_rows, nnz_cap) + 256;
+    if (need8 > need) need = need8;
+  }
+  return need;
 }
 
 extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_img, int H, int W,
@@ -815,19 +1316,43 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
   SPALIGN_REQUIRE(cap_img > 0, "overlap_csr: nnz_cap smaller than n_img");
   const int ncell = fh * fw;
   OverlapWs ws;
-  size_t need = carve(ws, nullptr, n_img, ncell, n_rows, nnz_cap) + 256;
+  size_t need = spalign_overlap_workspace_bytes(n_img, H, W, fh, fw, n_rows, nnz_cap);
   if (ws_bytes < need) {
     set_error("overlap_csr: workspace %zu < %zu bytes", ws_bytes, need);
     return SPALIGN_E_WORKSPACE;
   }
   void* aligned = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  const bool s8 = (H == 8 * fh) && (W == 8 * fw) &&
+                  (reinterpret_cast<size_t>(labels) % 16 == 0);
+  if (s8 && getenv("SPALIGN_K1_LEGACY") == nullptr) {
+    S8Ws w8;
+    carve_s8(w8, aligned, fh, fw, n_rows, nnz_cap);
+    init_s8_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, fh, fw, gy, gx, nnz_flags);
+    dim3 egrid((fw + TILE_W - 1) / TILE_W, (fh + TILE_H - 1) / TILE_H, n_img);
+    if (label_dtype == SPALIGN_I32)
+      emit_s8v2_kernel<int32_t><<<egrid, TILE_W * TILE_H, 0, stream>>>(
+          (const int32_t*)labels, H, W, fh, fw, sp_off, gy, w8, nnz_cap, nnz_flags);
+    else
+      emit_s8v2_kernel<int64_t><<<egrid, TILE_W * TILE_H, 0, stream>>>(
+          (const int64_t*)labels, H, W, fh, fw, sp_off, gy, w8, nnz_cap, nnz_flags);
+    const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
+    scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum);
+    scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum, n_tiles, indptr,
+                                                    nnz_flags, nnz_cap, w8.heavy_rows,
+                                                    w8.heavy_count, w8.heavy_cap, nullptr, 0,
+                                                    BUCKET_CAP);
+    spill_scatter_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, indptr, nnz_cap, nnz_flags);
+    rowsort_bucket_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
+        w8, indptr, n_rows, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags, ncell);
+    rowsort_heavy_s8_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(
+        w8, indptr, ncell, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags);
+    return check_launch("overlap_csr");
+  }
   carve(ws, aligned, n_img, ncell, n_rows, nnz_cap);
 
   init_kernel<<<2 * kNumSMs, 256, 0, stream>>>(ws.zero_begin, ws.zero_ints, sum_y, sum_x, n_rows,
                                                nnz_flags);
   dim3 egrid((ncell + EMIT_THREADS - 1) / EMIT_THREADS, n_img);
-  const bool s8 = (H == 8 * fh) && (W == 8 * fw) &&
-                  (reinterpret_cast<size_t>(labels) % 16 == 0);
   if (label_dtype == SPALIGN_I32) {
     if (s8)
       emit_s8_kernel<int32_t><<<egrid, EMIT_THREADS, 0, stream>>>(
@@ -852,7 +1377,7 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
   scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum, n_tiles,
                                                   indptr, nnz_flags, nnz_cap, ws.heavy_rows,
                                                   ws.heavy_count, ws.heavy_cap, ws.pair_count,
-                                                  n_img);
+                                                  n_img, WARP_TIER_MAX);
   int sgx = (cap_img + 256 * 4 - 1) / (256 * 4);
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
@@ -924,7 +1449,7 @@ extern "C" int spalign_overlap_bilinear_csr(
   scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(ws.row_nnz, n_rows, ws.tile_sum, n_tiles,
                                                   indptr, nnz_flags, nnz_cap, ws.heavy_rows,
                                                   ws.heavy_count, ws.heavy_cap, ws.pair_count,
-                                                  n_img);
+                                                  n_img, WARP_TIER_MAX);
   int sgx = (cap_img + 256 * 4 - 1) / (256 * 4);
   sgx = sgx < 1 ? 1 : (sgx > 64 ? 64 : sgx);
   scatter_kernel<<<dim3(sgx, n_img), 256, 0, stream>>>(ws, cap_img, indptr, nnz_cap, nnz_flags);
