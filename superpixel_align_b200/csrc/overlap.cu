@@ -789,6 +789,7 @@ struct S8Ws {
   double* gxT;       // [fw][32]
   double* gx8;       // [fw]
   double* gy8;       // [fh]
+  double* gyT;       // [8][fh]: gy of pixel row r of cell row cy at gyT[r * fh + cy]
 };
 
 size_t carve_s8(S8Ws& ws, void* base, int fh, int fw, int64_t R, int64_t cap) {
@@ -817,6 +818,7 @@ size_t carve_s8(S8Ws& ws, void* base, int fh, int fw, int64_t R, int64_t cap) {
   ws.gxT = c.take<double>((size_t)fw * 32);
   ws.gx8 = c.take<double>(fw);
   ws.gy8 = c.take<double>(fh);
+  ws.gyT = c.take<double>((size_t)8 * fh);
   return c.used();
 }
 
@@ -851,7 +853,10 @@ __global__ void init_s8_kernel(S8Ws ws, int fh, int fw, const double* __restrict
   for (size_t k = i; k < (size_t)fh; k += stride) {
     double sum = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum = __dadd_rn(sum, gy[k * 8 + j]);
+    for (int j = 0; j < 8; ++j) {
+      sum = __dadd_rn(sum, gy[k * 8 + j]);
+      ws.gyT[(size_t)j * fh + k] = gy[k * 8 + j];
+    }
     ws.gy8[k] = sum;
   }
 }
@@ -866,7 +871,7 @@ __device__ __forceinline__ void store_pair(const S8Ws& ws, int row, int pos, con
       ws.t_row[sp] = row;
       ws.t_col[sp] = e.x;
       ws.t_cnt[sp] = e.y;
-      ws.t_prior[sp] = __hiloint2double(e.w, e.z);
+      ws.t_prior[sp] = __hiloint2double(e.w, e.z);  // the pixel mask, bit pattern only
     } else {
       atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
                (unsigned long long)SPALIGN_F_NNZ_OVERFLOW);
@@ -878,125 +883,163 @@ __device__ __forceinline__ void place_pair(const S8Ws& ws, int row, const int4& 
   store_pair(ws, row, atomicAdd(&ws.cursor[row], 1), e, spill_cap, nnz_flags);
 }
 
+// bit j of the result = (v[j] == L): one compare and one predicated OR per pixel
+__device__ __forceinline__ void mask_or_eq(unsigned& acc, int v, int L, unsigned bit) {
+  asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q or.b32 %0, %0, %3; }"
+      : "+r"(acc)
+      : "r"(v), "r"(L), "r"(bit));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#ifndef EMIT_CELLS_PER_THREAD
+#define EMIT_CELLS_PER_THREAD 8
+#endif
+constexpr int EMIT_CELLS = EMIT_CELLS_PER_THREAD;  // cells per thread (16-cell tiles along x)
+
 template <typename LabelT>
 __global__ void __launch_bounds__(TILE_W * TILE_H, EMIT2_MIN_BLOCKS)
 emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
-                 const int64_t* __restrict__ sp_off, const double* __restrict__ gy, S8Ws ws,
-                 int64_t spill_cap, int64_t* nnz_flags) {
-  // pairs of this thread's cell wait here until all of them are known, then their slot atomics
-  // are issued back to back (one exposed round trip per cell instead of one per label)
-  constexpr int PEND = 4;
-  __shared__ int4 s_pend[PEND][TILE_W * TILE_H];
-  __shared__ int s_prow[PEND][TILE_W * TILE_H];
+                 const int64_t* __restrict__ sp_off, S8Ws ws, int64_t spill_cap,
+                 int64_t* nnz_flags) {
+  // Software pipeline per thread, no block barrier anywhere: the labels of the NEXT cell travel
+  // global -> shared memory with cp.async while the current cell is processed out of registers;
+  // the pairs of a cell wait in shared memory until all of them are known, their slot atomics
+  // are issued back to back, and the returned slots are only consumed after the first pass
+  // over the next cell.
+  constexpr int PEND = 4, NT = TILE_W * TILE_H;
+  constexpr int CH = 64 * (int)sizeof(LabelT) / 16;  // 16-byte chunks per cell
+  extern __shared__ int4 s_dyn[];
+  int4 (*s_lab)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn);  // [chunk][thread]: conflict-free
+  int4 (*s_pend)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn + CH * NT);
+  int (*s_prow)[NT] = reinterpret_cast<int (*)[NT]>(s_dyn + (CH + PEND) * NT);
   const int t = threadIdx.x, tx = t & (TILE_W - 1), ty = t / TILE_W;
   const int img = blockIdx.z;
-  const int cx = blockIdx.x * TILE_W + tx, cy = blockIdx.y * TILE_H + ty;
-  const bool have_prior = gy != nullptr;
-  if (cx >= fw || cy >= fh) return;
-  const int c = cy * fw + cx;
-  const LabelT* p = labels + ((size_t)img * H + (size_t)cy * 8) * W + (size_t)cx * 8;
-  int v[64];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if (sizeof(LabelT) == 4) {
-      // (L1-allocating loads: mixed cells re-read single pixels below)
-      const int4 a = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
-      const int4 b = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + 1);
-      v[r * 8 + 0] = a.x; v[r * 8 + 1] = a.y; v[r * 8 + 2] = a.z; v[r * 8 + 3] = a.w;
-      v[r * 8 + 4] = b.x; v[r * 8 + 5] = b.y; v[r * 8 + 6] = b.z; v[r * 8 + 7] = b.w;
-    }
-  }
+  const int cy = blockIdx.y * TILE_H + ty;
+  const int cx0 = blockIdx.x * (TILE_W * EMIT_CELLS) + tx;
+  if (cy >= fh || cx0 >= fw) return;
   const int64_t row0 = sp_off[img];
   const int n_sp = (int)(sp_off[img + 1] - row0);
-  if (sizeof(LabelT) == 8) {
+  const LabelT* prow = labels + ((size_t)img * H + (size_t)cy * 8) * W;
+  constexpr int PER_ROW = 8 * (int)sizeof(LabelT) / 16;  // chunks per pixel row of a cell
+  auto prefetch = [&](int cx) {
+    const char* src = reinterpret_cast<const char*>(prow + (size_t)cx * 8);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const longlong2* q = reinterpret_cast<const longlong2*>(p + (size_t)r * W);
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        longlong2 a = __ldg(q + h);
-        v[r * 8 + 2 * h] = (a.x >= 0 && a.x < n_sp) ? (int)a.x : -1;
-        v[r * 8 + 2 * h + 1] = (a.y >= 0 && a.y < n_sp) ? (int)a.y : -1;
+      for (int h = 0; h < PER_ROW; ++h)
+        cp_async16(&s_lab[r * PER_ROW + h][t], src + ((size_t)r * W) * sizeof(LabelT) + h * 16);
+    cp_async_commit();
+  };
+  prefetch(cx0);
+  int npend = 0, pos[PEND];
+  bool bad = false;
+#pragma unroll 1
+  for (int it = 0; it < EMIT_CELLS; ++it) {
+    const int cx = cx0 + it * TILE_W;
+    // lanes leave the label loop below at different times: without this barrier the warp stays
+    // split into sub-warps for all following cells (measured: 1.7x the instructions)
+    __syncwarp();
+    if (cx >= fw) continue;
+    const int c = cy * fw + cx;
+    const LabelT* p = prow + (size_t)cx * 8;
+    int v[64];
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int4 q = s_lab[k][t];
+      if (sizeof(LabelT) == 4) {
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+      } else {
+        const long long a = ((long long)q.y << 32) | (unsigned)q.x;
+        const long long b2 = ((long long)q.w << 32) | (unsigned)q.z;
+        v[2 * k] = (a >= 0 && a < n_sp) ? (int)a : -1;
+        v[2 * k + 1] = (b2 >= 0 && b2 < n_sp) ? (int)b2 : -1;
       }
     }
+    if (it + 1 < EMIT_CELLS && cx + TILE_W < fw) prefetch(cx + TILE_W);
+    unsigned long long remaining = ~0ull;
+    int L = v[0];
+    int npend_prev = npend;  // pairs of the previous cell whose slot atomics are in flight
+    npend = 0;
+    while (true) {
+      unsigned lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        mask_or_eq(lo0, v[j], L, 1u << j);
+        mask_or_eq(lo1, v[j + 1], L, 2u << j);
+        mask_or_eq(hi0, v[32 + j], L, 1u << j);
+        mask_or_eq(hi1, v[33 + j], L, 2u << j);
+      }
+      const unsigned lo = lo0 | lo1, hi = hi0 | hi1;
+      const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      remaining &= ~m;
+      // next label: an uncovered pixel among a few fixed positions (corners, edge and centre
+      // pixels: static register indices), else the first uncovered pixel re-read from L2
+      int nextl = 0;
+      bool found = false;
+#define SPALIGN_CAND(q)                          \
+  if (!found && ((remaining >> (q)) & 1ull)) {   \
+    nextl = v[q];                                \
+    found = true;                                \
   }
-  const double* gxT = ws.gxT + (size_t)cx * 32;
-  const double cell_prior = have_prior ? __dmul_rn(ws.gy8[cy], ws.gx8[cx]) : 0.0;
-  unsigned long long remaining = ~0ull;
-  double emitted_prior = 0.0;
-  bool can_complement = true, bad = false;
-  int npend = 0;
-  int L = v[0];
-  while (true) {
-    unsigned lo = 0, hi = 0;
+      SPALIGN_CAND(63) SPALIGN_CAND(7) SPALIGN_CAND(56) SPALIGN_CAND(36) SPALIGN_CAND(27)
+      SPALIGN_CAND(60) SPALIGN_CAND(3) SPALIGN_CAND(39) SPALIGN_CAND(24)
+#undef SPALIGN_CAND
+      if (remaining != 0ull && !found) {
+        const int i = __ffsll((long long)remaining) - 1;
+        const LabelT nextq = __ldcg(p + (size_t)(i >> 3) * W + (i & 7));
+        nextl = (sizeof(LabelT) == 4) ? (int)nextq
+                                      : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
+      }
+      if (npend_prev) {
+        // the previous cell's slots have had a whole pass to come back: store its pairs
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (v[j] == L) lo |= 1u << j;
-      if (v[32 + j] == L) hi |= 1u << j;
-    }
-    const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    remaining &= ~m;
-    // next label: the first pixel not covered yet (re-read, L1 hit; issued before the work on
-    // the current label so that its latency hides behind it)
-    LabelT nextq = 0;
-    if (remaining != 0ull) {
-      const int i = __ffsll((long long)remaining) - 1;
-      nextq = __ldg(p + (size_t)(i >> 3) * W + (i & 7));
-    }
-    if ((unsigned)L < (unsigned)n_sp) {
-      const int cnt = __popc(lo) + __popc(hi);
-      int packed = PACKED_FULL;
-      double pr = cell_prior;
-      if (cnt != 64) {
-        // bit i = pixel row i >> 3, column i & 7: sums of the offsets of the set bits
-        const int sxl = __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) +
-                        4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull);
-        const int syl = __popcll(m & 0xff00ff00ff00ff00ull) + 2 * __popcll(m & 0xffff0000ffff0000ull) +
-                        4 * __popcll(m & 0xffffffff00000000ull);
-        packed = cnt | (syl << 7) | (sxl << 15);
-        if (have_prior) {
-          if (remaining == 0ull && can_complement) {
-            // last label of the cell: whole-cell prior minus what the other labels took
-            pr = __dadd_rn(cell_prior, -emitted_prior);
-          } else {
-            pr = 0.0;
+        for (int k = 0; k < PEND; ++k)
+          if (k < npend_prev) store_pair(ws, s_prow[k][t], pos[k], s_pend[k][t], spill_cap, nnz_flags);
+        npend_prev = 0;
+      }
+      if ((unsigned)L < (unsigned)n_sp) {
+        const int cnt = __popc(lo) + __popc(hi);
+        int packed = PACKED_FULL;
+        if (cnt != 64) {
+          // bit i = pixel row i >> 3, column i & 7: sums of the offsets of the set bits
+          const int sxl = __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) +
+                          4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull);
+          const int syl = __popcll(m & 0xff00ff00ff00ff00ull) + 2 * __popcll(m & 0xffff0000ffff0000ull) +
+                          4 * __popcll(m & 0xffffffff00000000ull);
+          packed = cnt | (syl << 7) | (sxl << 15);
+        }
+        if (npend == PEND) {  // more than PEND labels in one cell: place the oldest now
+          const int row = s_prow[0][t];
+          const int4 e = s_pend[0][t];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
-              const double rs = __dadd_rn(__ldg(gxT + (b & 15u)), __ldg(gxT + 16 + (b >> 4)));
-              pr = __fma_rn(__ldg(gy + cy * 8 + r), rs, pr);
-            }
-            emitted_prior = __dadd_rn(emitted_prior, pr);
+          for (int k = 0; k + 1 < PEND; ++k) {
+            s_prow[k][t] = s_prow[k + 1][t];
+            s_pend[k][t] = s_pend[k + 1][t];
           }
+          --npend;
+          place_pair(ws, row, e, spill_cap, nnz_flags);
         }
+        s_prow[npend][t] = (int)(row0 + L);
+        s_pend[npend][t] = make_int4(c, packed, (int)lo, (int)hi);
+        ++npend;
+      } else {  // label outside [0, n_sp): flag it, emit nothing
+        bad = true;
       }
-      if (npend == PEND) {  // more than PEND labels in one cell: place the oldest now
-        const int row = s_prow[0][t];
-        const int4 e = s_pend[0][t];
-#pragma unroll
-        for (int k = 0; k + 1 < PEND; ++k) {
-          s_prow[k][t] = s_prow[k + 1][t];
-          s_pend[k][t] = s_pend[k + 1][t];
-        }
-        --npend;
-        place_pair(ws, row, e, spill_cap, nnz_flags);
-      }
-      s_prow[npend][t] = (int)(row0 + L);
-      s_pend[npend][t] = make_int4(c, packed, __double2loint(pr), __double2hiint(pr));
-      ++npend;
-    } else {  // label outside [0, n_sp): flag it, emit nothing
-      bad = true;
-      can_complement = false;
+      if (remaining == 0ull) break;
+      L = nextl;
     }
-    if (remaining == 0ull) break;
-    L = (sizeof(LabelT) == 4) ? (int)nextq
-                              : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
-  }
-  // slot atomics of all pairs of the cell, back to back, then the 16-byte bucket stores
-  int pos[PEND];
+    // slot atomics of all pairs of the cell, back to back; consumed during the next cell
 #pragma unroll
-  for (int k = 0; k < PEND; ++k)
-    if (k < npend) pos[k] = atomicAdd(&ws.cursor[s_prow[k][t]], 1);
+    for (int k = 0; k < PEND; ++k)
+      if (k < npend) pos[k] = atomicAdd(&ws.cursor[s_prow[k][t]], 1);
+  }
 #pragma unroll
   for (int k = 0; k < PEND; ++k)
     if (k < npend) store_pair(ws, s_prow[k][t], pos[k], s_pend[k][t], spill_cap, nnz_flags);
@@ -1022,15 +1065,36 @@ spill_scatter_kernel(S8Ws ws, const int* __restrict__ indptr, int64_t nnz_cap,
   }
 }
 
-__device__ __forceinline__ double int4_prior(const int4& e) {
-  return __hiloint2double(e.w, e.z);
+// Prior mass of one pair from its pixel mask (lo = pixel rows 0..3, hi = rows 4..7, one byte per
+// row): sum_r gy[r] * (sum of gx over the row's set columns), the inner sums looked up in the
+// nibble tables of the cell column.  A whole cell is gy8 * gx8.  Fixed evaluation order.
+struct PriorTabs {
+  const double* gyT;  // [8][fh] (lanes of a warp hold neighbouring cells: one line per load)
+  int fh;
+  const double* gxT;  // [fw][32]
+  const double* gx8;  // [fw]
+  const double* gy8;  // [fh]
+};
+__device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
+                                             unsigned lo, unsigned hi) {
+  if (packed_cnt(packed) == 64) return __dmul_rn(__ldg(pt.gy8 + cyy), __ldg(pt.gx8 + cxx));
+  const double* T = pt.gxT + (size_t)cxx * 32;
+  const double* g = pt.gyT + cyy;
+  double pr = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
+    const double rs = __dadd_rn(__ldg(T + (b & 15u)), __ldg(T + 16 + (b >> 4)));
+    pr = __fma_rn(__ldg(g + (size_t)r * pt.fh), rs, pr);
+  }
+  return pr;
 }
 
 // one warp per row of <= BUCKET_CAP cells, straight out of the bucket
 __global__ void __launch_bounds__(256)
 rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int* counts,
                       int* area, int64_t* sum_y, int64_t* sum_x, double* sum_prior,
-                      const int64_t* __restrict__ nnz_flags, int ncell) {
+                      const int64_t* __restrict__ nnz_flags, int ncell, PriorTabs pt) {
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
   const int lane = lane_id();
@@ -1098,7 +1162,8 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       a_sum = cn;
       y_sum = (long long)cn * (cyy * 8) + packed_sy(e.y);
       x_sum = (long long)cn * (cxx * 8) + packed_sx(e.y);
-      ps = __dadd_rn(0.0, int4_prior(e));
+      if (sum_prior != nullptr)
+        ps = __dadd_rn(0.0, pair_prior(pt, cyy, cxx, e.y, (unsigned)e.z, (unsigned)e.w));
     }
     if (lane + 32 < L) {
       const int4 e = bk[k1 & 127u];
@@ -1108,8 +1173,10 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       a_sum += cn;
       y_sum += (long long)cn * (cyy * 8) + packed_sy(e.y);
       x_sum += (long long)cn * (cxx * 8) + packed_sx(e.y);
-      pv1 = int4_prior(e);
-      ps = __dadd_rn(ps, pv1);
+      if (sum_prior != nullptr) {
+        pv1 = pair_prior(pt, cyy, cxx, e.y, (unsigned)e.z, (unsigned)e.w);
+        ps = __dadd_rn(ps, pv1);
+      }
     }
   } else {
     double* sorted_prior = ws.u_prior;  // this row's CSR range is unused by the heavy tier
@@ -1130,7 +1197,8 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
         const int cn = packed_cnt(me.y), cyy = me.x / fw, cxx = me.x - cyy * fw;
         indices[base + rank] = me.x;
         counts[base + rank] = cn;
-        sorted_prior[base + rank] = int4_prior(me);
+        if (sum_prior != nullptr)
+          sorted_prior[base + rank] = pair_prior(pt, cyy, cxx, me.y, (unsigned)me.z, (unsigned)me.w);
         a_sum += cn;
         y_sum += (long long)cn * (cyy * 8) + packed_sy(me.y);
         x_sum += (long long)cn * (cxx * 8) + packed_sx(me.y);
@@ -1160,7 +1228,7 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
 __global__ void __launch_bounds__(HEAVY_THREADS)
 rowsort_heavy_s8_kernel(S8Ws ws, const int* __restrict__ indptr, int ncell, int fw, int* indices,
                         int* counts, int* area, int64_t* sum_y, int64_t* sum_x,
-                        double* sum_prior, const int64_t* __restrict__ nnz_flags) {
+                        double* sum_prior, const int64_t* __restrict__ nnz_flags, PriorTabs pt) {
   if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
   const int n_heavy = min(*ws.heavy_count, ws.heavy_cap);
   int* d_cnt = ws.d_cnt + (size_t)blockIdx.x * ncell;
@@ -1181,7 +1249,7 @@ rowsort_heavy_s8_kernel(S8Ws ws, const int* __restrict__ indptr, int ncell, int 
       double pv;
       if (e < BUCKET_CAP) {
         const int4 q = bk[e];
-        c = q.x; pk = q.y; pv = int4_prior(q);
+        c = q.x; pk = q.y; pv = __hiloint2double(q.w, q.z);  // the mask bits
       } else {
         c = ws.u_col[base + e]; pk = ws.u_cnt[base + e]; pv = ws.u_prior[base + e];
       }
@@ -1206,7 +1274,11 @@ rowsort_heavy_s8_kernel(S8Ws ws, const int* __restrict__ indptr, int ncell, int 
         a_sum += cn;
         y_sum += (long long)cn * (cyy * 8) + packed_sy(pk);
         x_sum += (long long)cn * (cxx * 8) + packed_sx(pk);
-        p_sum = __dadd_rn(p_sum, d_prior[c]);
+        if (sum_prior != nullptr) {
+          const double mb = d_prior[c];  // mask bits
+          p_sum = __dadd_rn(p_sum, pair_prior(pt, cyy, cxx, pk, (unsigned)__double2loint(mb),
+                                              (unsigned)__double2hiint(mb)));
+        }
       }
       running += total;
     }
@@ -1328,13 +1400,22 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
     S8Ws w8;
     carve_s8(w8, aligned, fh, fw, n_rows, nnz_cap);
     init_s8_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, fh, fw, gy, gx, nnz_flags);
-    dim3 egrid((fw + TILE_W - 1) / TILE_W, (fh + TILE_H - 1) / TILE_H, n_img);
-    if (label_dtype == SPALIGN_I32)
-      emit_s8v2_kernel<int32_t><<<egrid, TILE_W * TILE_H, 0, stream>>>(
-          (const int32_t*)labels, H, W, fh, fw, sp_off, gy, w8, nnz_cap, nnz_flags);
-    else
-      emit_s8v2_kernel<int64_t><<<egrid, TILE_W * TILE_H, 0, stream>>>(
-          (const int64_t*)labels, H, W, fh, fw, sp_off, gy, w8, nnz_cap, nnz_flags);
+    dim3 egrid((fw + TILE_W * EMIT_CELLS - 1) / (TILE_W * EMIT_CELLS), (fh + TILE_H - 1) / TILE_H,
+               n_img);
+    constexpr int NT = TILE_W * TILE_H;
+    if (label_dtype == SPALIGN_I32) {
+      const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4);
+      SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int32_t>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      emit_s8v2_kernel<int32_t><<<egrid, NT, smem, stream>>>(
+          (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags);
+    } else {
+      const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4);
+      SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int64_t>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      emit_s8v2_kernel<int64_t><<<egrid, NT, smem, stream>>>(
+          (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags);
+    }
     const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
     scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum);
     scan_finish_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum, n_tiles, indptr,
@@ -1342,10 +1423,12 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
                                                     w8.heavy_count, w8.heavy_cap, nullptr, 0,
                                                     BUCKET_CAP);
     spill_scatter_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, indptr, nnz_cap, nnz_flags);
+    const PriorTabs pt{w8.gyT, fh, w8.gxT, w8.gx8, w8.gy8};
     rowsort_bucket_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
-        w8, indptr, n_rows, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags, ncell);
+        w8, indptr, n_rows, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags, ncell,
+        pt);
     rowsort_heavy_s8_kernel<<<HEAVY_SLOTS, HEAVY_THREADS, 0, stream>>>(
-        w8, indptr, ncell, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags);
+        w8, indptr, ncell, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags, pt);
     return check_launch("overlap_csr");
   }
   carve(ws, aligned, n_img, ncell, n_rows, nnz_cap);
