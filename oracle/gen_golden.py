@@ -149,6 +149,83 @@ def gen_overlap():
     print('overlap_oracle.npz ok')
 
 
+def gen_refine():
+    """The reference's INLINE overlap-refine loop (superpixel_overlaps.py:360-369), run
+    unmodified through ref_extract.load_inline: cell-level road masks (nearest-upsampled by the
+    reference's own cv.resize call, :362), stride-8 and non-integer-ratio geometries, an image
+    without predicted road, thresholds around the decision.  Anchors the overlap counts
+    (M @ road_mask) to reference code."""
+    import types
+    ref_refine = ref_extract.refine_loop()
+    out = {}
+    rs = np.random.RandomState(11)
+    cases = [('s8', 64, 96, 8, 12, 4, 6), ('ratio', 50, 70, 7, 9, 3, 4), ('r224', 224, 224, 28, 28, 7, 7)]
+    for name, H, W, fh, fw, gy, gx in cases:
+        lab = synth.voronoi_labels(H, W, gy, gx, image_index=21)
+        road = rs.rand(fh, fw) < 0.35
+        out[name + '__label'] = lab
+        out[name + '__road_cell'] = road
+        out[name + '__fh'], out[name + '__fw'] = fh, fw
+        for thr in (0.01, 0.05, 0.2):
+            (refined,) = ref_refine(road.copy(), lab, types.SimpleNamespace(overlap_threshold=thr))
+            out['%s__refined_%g' % (name, thr)] = np.asarray(refined, dtype=np.uint8)
+    lab = synth.voronoi_labels(64, 96, 4, 6, image_index=22)
+    (refined,) = ref_refine(np.zeros((8, 12), dtype=bool), lab, types.SimpleNamespace(overlap_threshold=0.01))
+    out['noroad__label'], out['noroad__refined'] = lab, np.asarray(refined, dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'refine_ref.npz'), **out)
+    print('refine_ref.npz:', sorted(k for k in out if 'refined' in k))
+
+
+def gen_direct():
+    """The reference's INLINE direct feature build (direct_clustering.py:298-303: concat,
+    (x, y) cell-index columns, transpose to rows) and prior tiling (:307-308), then its
+    kmeans() on the result -- the whole direct_clustering path on a 2-image batch."""
+    import types
+    build = ref_extract.direct_feature_build()
+    tile = ref_extract.direct_prior_tiling()
+    refd = ref_extract.load('direct_clustering.py', seed=1111)
+    feats = np.stack([synth.smooth_features(12, 9, 14, seed=40 + i, radius=1) for i in range(2)])
+    X, n, h, w = build([feats], np)
+    args = types.SimpleNamespace(y_rel_pos=0.75, x_rel_pos=0.5, y_rel_sigma=0.1, x_rel_sigma=0.1)
+    (prior,) = tile(h, w, n, args)
+    state = np.random.get_state()
+    assign = refd.kmeans(4, X, prior)
+    np.random.set_state(state)
+    from oracle import spalign_oracle as so
+    init = so.kmeans_init(4, prior)
+    np.savez_compressed(os.path.join(OUT, 'direct_features_ref.npz'), feats=feats, X=X, prior=prior,
+                        n=n, h=h, w=w, init=init.astype(np.int32),
+                        assign=np.asarray(assign).astype(np.int32))
+    print('direct_features_ref.npz:', X.shape, X.dtype, int(np.asarray(assign).max()))
+
+
+def gen_gapped():
+    """Label ids with gaps (1-based ids as skimage >= 0.19 slic yields, plus a missing id):
+    the reference's create_prior / weighted_kmeans on them.  Rows follow np.unique order
+    (:124, :226); the paint-back addresses pixels by the enumerate index (:195-198), so pixels
+    whose label value is >= n_i keep 0."""
+    ref = ref_extract.load('batch_spalign_kmeans.py', seed=1111)
+    H, W = 32, 64
+    labs = np.stack([synth.voronoi_labels(H, W, 3, 5, image_index=30 + i, dtype=np.int64)
+                     for i in range(2)]) + 1
+    labs[1][labs[1] >= 7] += 2          # ids 7, 8 missing in image 1
+    n_per = [len(np.unique(l)) for l in labs]
+    w = np.concatenate([ref.create_prior(l, 0.75, 0.5, 0.1, 0.1) for l in labs])
+    rs = np.random.RandomState(3)
+    feats = (rs.standard_normal((3, 6)) * 3)[rs.randint(0, 3, sum(n_per))] + \
+        rs.standard_normal((sum(n_per), 6))
+    feats = feats.astype(np.float32).astype(np.float64)
+    state = np.random.get_state()
+    cres, road = ref.weighted_kmeans(labs, feats, w, 3, n_per)
+    np.random.set_state(state)
+    from oracle import spalign_oracle as so
+    init = so.kmeans_init(3, w)
+    np.savez_compressed(os.path.join(OUT, 'gapped_ref.npz'), labs=labs, n_per=np.array(n_per),
+                        weights=w, feats=feats, k=3, init=init.astype(np.int32), cluster_map=cres,
+                        road=road)
+    print('gapped_ref.npz:', n_per, cres.shape)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     random.seed(1111)
@@ -156,3 +233,6 @@ if __name__ == '__main__':
     gen_prior()
     gen_weighted_kmeans()
     gen_overlap()
+    gen_refine()
+    gen_direct()
+    gen_gapped()

@@ -56,6 +56,92 @@ class _Chainer:
         pass
 
 
+class _Concat:
+    """chainer.functions.concat shim: ``F.concat(xs, axis).array``."""
+
+    def __init__(self, xs, axis=1):
+        self.array = np.concatenate([np.asarray(getattr(x, 'array', x)) for x in xs], axis=axis)
+
+
+class _F:
+    concat = _Concat
+
+
+def _statements_in(tree, func: str, first: int, last: int):
+    """The statement nodes of ``func`` whose source lines lie inside [first, last]: the
+    shallowest body list that holds statements entirely inside the range."""
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == func)
+
+    def search(body):
+        hit = [st for st in body if st.lineno >= first and st.end_lineno <= last]
+        if hit:
+            return hit
+        for st in body:
+            if st.lineno <= first and st.end_lineno >= last:
+                for field in ('body', 'orelse', 'finalbody'):
+                    sub = getattr(st, field, None)
+                    if sub:
+                        got = search(sub)
+                        if got:
+                            return got
+        return []
+    return search(fn.body)
+
+
+def load_inline(script: str, func: str, first: int, last: int, name: str, args, returns):
+    """Wrap the INLINE statements ``first..last`` of the reference function ``func`` into a
+    function ``name(*args) -> returns`` and return it: the reference code runs unmodified (the
+    statement nodes are taken from the parsed source, nothing is retyped), only the ``def``
+    line and the ``return`` are added.  Used for the overlap-refine loop
+    (superpixel_overlaps.py:360-369) and the direct feature build / prior tiling
+    (direct_clustering.py:298-308), which the reference does not factor into functions."""
+    if not available():
+        raise FileNotFoundError('reference tree not found at %s' % REFERENCE_ROOT)
+    path = os.path.join(REFERENCE_ROOT, script)
+    with open(path) as fp:
+        tree = ast.parse(fp.read(), filename=path)
+    body = _statements_in(tree, func, first, last)
+    if not body or body[0].lineno != first or body[-1].end_lineno != last:
+        raise ValueError('%s:%d-%d does not delimit whole statements of %s (got %s)'
+                         % (script, first, last, func,
+                            [(b.lineno, b.end_lineno) for b in body]))
+    ret = ast.Return(value=ast.Tuple(elts=[ast.Name(id=r, ctx=ast.Load()) for r in returns],
+                                     ctx=ast.Load()))
+    fdef = ast.FunctionDef(
+        name=name,
+        args=ast.arguments(posonlyargs=[], args=[ast.arg(arg=a) for a in args], kwonlyargs=[],
+                           kw_defaults=[], defaults=[]),
+        body=list(body) + [ret], decorator_list=[], type_params=[])
+    mod = ast.fix_missing_locations(ast.Module(body=[fdef], type_ignores=[]))
+    import cv2 as cv
+    # helper functions the statements call (create_prior, ...)
+    helpers = {}
+    if script in _WANTED:
+        helpers = vars(load(script, seed=None))
+    ns = {'np': np, 'cv': cv, 'F': _F, 'cuda': _Cuda, 'chainer': _Chainer, **helpers}
+    exec(compile(mod, path, 'exec'), ns)
+    return ns[name]
+
+
+def refine_loop():
+    """superpixel_overlaps.py:360-369 as ``f(road_mask, superpixel, args) -> (refined_roadmap,)``
+    (road_mask: bool/uint8 cell or pixel mask of one image, superpixel: its label map)."""
+    return load_inline('superpixel_overlaps.py', 'estimate_road_mask', 360, 369,
+                       'ref_refine', ['road_mask', 'superpixel', 'args'], ['refined_roadmap'])
+
+
+def direct_feature_build():
+    """direct_clustering.py:298-303 as ``f(use_maps, xp) -> (feature_maps, n, h, w)``."""
+    return load_inline('direct_clustering.py', 'estimate_road_mask', 298, 303,
+                       'ref_direct_features', ['use_maps', 'xp'], ['feature_maps', 'n', 'h', 'w'])
+
+
+def direct_prior_tiling():
+    """direct_clustering.py:307-308 as ``f(h, w, n, args) -> (prior,)``."""
+    return load_inline('direct_clustering.py', 'estimate_road_mask', 307, 308,
+                       'ref_direct_prior', ['h', 'w', 'n', 'args'], ['prior'])
+
+
 def load(script: str = 'batch_spalign_kmeans.py', seed: int | None = 1111) -> types.SimpleNamespace:
     """Return a namespace holding the reference functions of ``script``.
 

@@ -14,10 +14,19 @@ All arithmetic runs in libspalign_b200.so on the GPU; there is no CPU fallback.
 Differences from the reference, by design:
   * ``superpixel_align`` pools with the exact superpixel x cell pixel-count matrix (mean of
     the nearest-upsampled feature map over ALL member pixels) instead of 10 randomly sampled
-    anchors; ``n_select`` / ``n_neighbor`` are accepted and ignored.  The centroid columns are
-    identical to the reference's (exact integer sums / area).
-  * labels must be contiguous ids 0..S-1 per image (what skimage's slic/felzenszwalb return
-    and what the reference's paint-back assumes, :195-198).
+    anchors; ``n_select`` / ``n_neighbor`` are accepted and ignored.  The centroid columns of
+    the arrays handed back to NumPy callers are the reference's (exact integer sums / area in
+    float64, == scipy center_of_mass); the device-resident descriptors keep them in float32
+    (<= 1.2e-4 px rounding at x ~ 2000), which only matters for near-ties of the clustering.
+  * label ids with gaps (e.g. skimage >= 0.19 ``slic`` starts at 1) follow the reference: rows
+    are the sorted unique ids (:226, :124), the paint-back addresses pixels by the enumerate
+    index (:195-198).
+
+State shared by the three ``batch_*`` calls of one batch (label maps on the device, overlap
+matrix, prior sums): pass the object returned by ``prepare_batch`` in place of ``superpixels``
+for the sync-free route, or keep passing the array -- then the state is found again through
+the array's identity AND content (torch: ``_version``; NumPy: a checksum of the buffer), so a
+preallocated buffer refilled in place is never mistaken for the previous batch.
 """
 from __future__ import annotations
 
@@ -28,7 +37,7 @@ import torch
 
 from . import _lib, ops
 
-__all__ = ['create_prior', 'weighted_average', 'kmeans', 'weighted_kmeans', 'superpixel_align',
+__all__ = ['BatchState', 'prepare_batch', 'create_prior', 'weighted_average', 'kmeans', 'weighted_kmeans', 'superpixel_align',
            'batch_superpixel_align', 'batch_create_prior', 'batch_weighted_kmeans',
            'estimate_road_mask']
 
@@ -78,49 +87,93 @@ def _prior_from_args(args):
         return None
 
 
-class _BatchState:
+class BatchState:
     """Device-side state of one batch of label maps, shared by the three batch_* calls the
     reference makes on the same ``superpixels`` array (batch_spalign_kmeans.py:444-457)."""
 
     def __init__(self, superpixels, dev, fh, fw, prior):
-        self.labels = _labels_to_dev(superpixels, dev)
-        if self.labels.dim() == 2:
-            self.labels = self.labels[None]
+        self.raw_labels = _labels_to_dev(superpixels, dev)
+        if self.raw_labels.dim() == 2:
+            self.raw_labels = self.raw_labels[None]
+        self.labels = self.raw_labels
         self.n_sp = (ops.label_max(self.labels).cpu().numpy().astype(np.int64) + 1)  # sync
         self.fh, self.fw, self.prior = fh, fw, prior
         self.ov = ops.overlap_csr(self.labels, fh, fw, self.n_sp, prior=prior, retry=True)
         self.ov.validate()
+        if self.ov.has_empty_rows:
+            # ids with gaps: the reference enumerates np.sort(np.unique(superpixels)) (:226,
+            # :124, :321), so rows are the sorted unique ids.  Off the fast path (sync + sort).
+            compact, n_sp = [], []
+            for i in range(self.labels.shape[0]):
+                u, inv = torch.unique(self.labels[i], sorted=True, return_inverse=True)
+                compact.append(inv.to(self.labels.dtype))
+                n_sp.append(int(u.numel()))
+            self.labels = torch.stack(compact)
+            self.n_sp = np.asarray(n_sp, dtype=np.int64)
+            self.ov = ops.overlap_csr(self.labels, fh, fw, self.n_sp, prior=prior, retry=True)
+            self.ov.validate()
+        self.feat = None          # device descriptors of the last batch_superpixel_align
+        self.feat_token = None    # fingerprint of the array handed to the caller
 
 
+_BatchState = BatchState   # former private name
 _CACHE = {}
 
 
-def _key(superpixels):
-    sp = _unwrap(superpixels)
+def _fingerprint(sp):
+    """Identity AND content of a label array: torch -> storage address + in-place version
+    counter; NumPy -> address + two wrap-around checksums of the whole buffer (about 10 GB/s).
+    ``None`` = do not cache (lists, non-contiguous views, anything else)."""
     if isinstance(sp, torch.Tensor):
-        return ('t', sp.data_ptr(), tuple(sp.shape), sp.dtype)
-    sp = np.asarray(sp)
-    return ('n', sp.__array_interface__['data'][0], sp.shape, sp.dtype.str)
+        return ('t', sp.data_ptr(), tuple(sp.shape), sp.dtype, sp._version, str(sp.device))
+    if isinstance(sp, np.ndarray) and sp.flags.c_contiguous and sp.dtype.itemsize in (4, 8) \
+            and sp.size > 0:
+        v = sp.reshape(-1).view(np.uint32 if sp.dtype.itemsize == 4 else np.uint64)
+        with np.errstate(over='ignore'):
+            s1 = int(v.sum(dtype=np.uint64))
+            s2 = int(v[1::3].sum(dtype=np.uint64))
+        return ('n', sp.__array_interface__['data'][0], sp.shape, sp.dtype.str, s1, s2)
+    return None
 
 
 def _batch_state(superpixels, dev, fh, fw, prior):
-    """Reuse the overlap matrix when the same label array comes back (same buffer, same
-    geometry).  A hit that lacks the prior recomputes."""
-    key = _key(superpixels) + (fh, fw)
-    ent = _CACHE.get(key)
-    if ent is not None:
-        ref, st = ent
-        if (ref is None or ref() is not None) and (prior is None or st.prior == prior):
-            return st
-    st = _BatchState(superpixels, dev, fh, fw, prior)
+    """The state of this batch: the caller's ``BatchState`` if one was passed, else the cached
+    one when the SAME array with the SAME content comes back (a hit that lacks the prior or has
+    another geometry recomputes), else a new one."""
     sp = _unwrap(superpixels)
-    try:
-        ref = weakref.ref(sp)
-    except TypeError:
-        ref = None
+    if isinstance(sp, BatchState):
+        if (fh is not None and (sp.fh, sp.fw) != (fh, fw)) or \
+                (prior is not None and sp.prior != prior):
+            raise ValueError('BatchState was prepared for another feature grid / prior')
+        return sp
+    fp = _fingerprint(sp)
+    ent = _CACHE.get('state')
+    if fp is not None and ent is not None:
+        efp, ref, st = ent
+        if efp == fp and ref() is sp and (fh is None or (st.fh, st.fw) == (fh, fw)) and \
+                (prior is None or st.prior == prior):
+            return st
+    if fh is None:
+        fh, fw = _default_grid(sp)
+    st = BatchState(sp, dev, fh, fw, prior)
     _CACHE.clear()  # one batch at a time, like the reference loop
-    _CACHE[key] = (ref, st)
+    if fp is not None:
+        try:
+            _CACHE['state'] = (fp, weakref.ref(sp), st)
+        except TypeError:
+            pass
     return st
+
+
+def prepare_batch(args, superpixels, feature_shape=None):
+    """Explicit form of the shared state: upload the label maps once and build the overlap matrix
+    and prior sums.  Pass the result in place of ``superpixels`` to batch_superpixel_align /
+    batch_create_prior / batch_weighted_kmeans.  ``feature_shape`` = (fh, fw) of the feature
+    maps (default: DRN stride 8)."""
+    sp = _unwrap(superpixels)
+    dev = sp.device if isinstance(sp, torch.Tensor) and sp.is_cuda else _device(args)
+    fh, fw = feature_shape if feature_shape is not None else _default_grid(sp)
+    return BatchState(sp, dev, fh, fw, _prior_from_args(args))
 
 
 def clear_cache():
@@ -130,7 +183,7 @@ def clear_cache():
 def _default_grid(superpixels):
     """Feature grid assumed when only label maps are given: DRN stride 8."""
     sp = _unwrap(superpixels)
-    H, W = sp.shape[-2:]
+    H, W = np.shape(sp)[-2:]
     return max(1, H // 8), max(1, W // 8)
 
 
@@ -138,11 +191,10 @@ def _default_grid(superpixels):
 def create_prior(superpixels, y_rel_pos=0.75, x_rel_pos=0.5, y_rel_sigma=0.1, x_rel_sigma=0.2):
     """Mean Gaussian road prior per superpixel, sorted-label order, float64 [S]
     (batch_spalign_kmeans.py:111-129)."""
-    as_numpy = not isinstance(_unwrap(superpixels), torch.Tensor)
+    as_numpy = not isinstance(_unwrap(superpixels), (torch.Tensor, BatchState))
     dev = _device()
     prior = (y_rel_pos, x_rel_pos, y_rel_sigma, x_rel_sigma)
-    fh, fw = _default_grid(superpixels)
-    st = _batch_state(superpixels, dev, fh, fw, prior)
+    st = _batch_state(superpixels, dev, None, None, prior)
     w = st.ov.weights()
     return w.cpu().numpy() if as_numpy else w
 
@@ -198,6 +250,10 @@ def _kmeans_impl(k, X, weights, n_iter, init_assign):
         Xd = torch.from_numpy(np.ascontiguousarray(Xh)).to(dev)
     else:
         Xd = Xu if Xu.dtype in (torch.float32, torch.float64) else Xu.double()
+        if Xd.dtype == torch.float64:
+            X32 = Xd.float()
+            if bool((X32.double() == Xd).all()):   # lossless: use the fp32 path (one sync)
+                Xd = X32
     wu = _unwrap(weights)
     w_host = wu.detach().cpu().numpy() if isinstance(wu, torch.Tensor) else np.asarray(wu)
     w_host = w_host.astype(np.float64)
@@ -246,6 +302,25 @@ def _features_for(st, feature_maps, dev, append_pos, pooling=None):
     return ops.pool(cell, st.ov, append_pos=append_pos)
 
 
+def _features_to_host(st, feat, append_pos):
+    """Descriptors as the reference returns them (:270, :325-329): float32 without the centroid
+    columns; float64 with them, the centroid columns exact (integer sums / area in float64)."""
+    out = feat.cpu().numpy()
+    if not append_pos:
+        return out
+    out = out.astype(np.float64)
+    area = st.ov.area.to(torch.float64)
+    out[:, -2] = (st.ov.sum_y.to(torch.float64) / area).cpu().numpy()
+    out[:, -1] = (st.ov.sum_x.to(torch.float64) / area).cpu().numpy()
+    return out
+
+
+def _feature_token(a):
+    with np.errstate(over='ignore'):
+        v = a.reshape(-1).view(np.uint64)
+        return (a.__array_interface__['data'][0], a.shape, int(v.sum(dtype=np.uint64)))
+
+
 def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, append_pos=False,
                      pooling=None):
     """One descriptor per superpixel, [S, C(+2)] in sorted-label order
@@ -258,8 +333,7 @@ def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, a
     st = _batch_state(superpixels, dev, fh, fw, None)
     feat = _features_for(st, fm, dev, append_pos, pooling)
     if as_numpy:
-        out = feat.cpu().numpy()
-        return out.astype(np.float64) if append_pos else out  # reference dtypes (:270)
+        return _features_to_host(st, feat, append_pos)  # reference dtypes (:270)
     return feat
 
 
@@ -276,26 +350,22 @@ def batch_superpixel_align(args, model, imgs, superpixels, feature_maps):
     append_pos = not getattr(args, 'without_pos', False)
     feat = _features_for(st, fm, dev, append_pos, getattr(args, 'spalign_pooling', None))
     n_per = [int(v) for v in st.n_sp]
+    st.feat, st.feat_token = feat, None
     if as_numpy:
-        out = feat.cpu().numpy()
-        return (out.astype(np.float64) if append_pos else out), n_per
+        out = _features_to_host(st, feat, append_pos)
+        if out.dtype == np.float64:
+            st.feat_token = _feature_token(out)
+        return out, n_per
     return feat, n_per
 
 
 def batch_create_prior(args, superpixels):
     """float64 [sum S] prior weights -- batch_spalign_kmeans.py:333-344."""
     sp = _unwrap(superpixels)
-    as_numpy = not isinstance(sp, torch.Tensor)
-    dev = _device(args) if as_numpy else sp.device
-    prior = _prior_from_args(args)
-    key_hit = None
-    for key, (ref, st) in _CACHE.items():
-        if key[:4] == _key(superpixels) and st.prior == prior:
-            key_hit = st
-    if key_hit is None:
-        fh, fw = _default_grid(superpixels)
-        key_hit = _batch_state(superpixels, dev, fh, fw, prior)
-    w = key_hit.ov.weights()
+    as_numpy = not isinstance(sp, (torch.Tensor, BatchState))
+    dev = _device(args) if not isinstance(sp, torch.Tensor) else sp.device
+    st = _batch_state(superpixels, dev, None, None, _prior_from_args(args))
+    w = st.ov.weights()
     return w.cpu().numpy() if as_numpy else w
 
 
@@ -303,15 +373,36 @@ def weighted_kmeans(superpixels, superpixel_features, superpixel_weights, k,
                     n_superpixels_per_image, n_iter=1000, init_assign=None):
     """k-means over all superpixels of the batch jointly, then paint the cluster ids back
     (batch_spalign_kmeans.py:186-207).  Returns (clustering_result [N,H,W] in the label dtype,
-    clustering_result == 0)."""
+    clustering_result == 0).
+
+    The paint-back addresses pixels by their RAW label value (:195-198: ``superpixels == idx``
+    for idx in range(n_i)), like the reference; pixels whose label is >= n_i stay 0."""
     sp = _unwrap(superpixels)
-    as_numpy = not isinstance(sp, torch.Tensor)
-    dev = _device() if as_numpy else sp.device
-    labels = _labels_to_dev(sp, dev)
-    if labels.dim() == 2:
-        labels = labels[None]
-    assign = kmeans(k, _to_dev(superpixel_features, dev), superpixel_weights, n_iter=n_iter,
+    st = sp if isinstance(sp, BatchState) else None
+    feats = _unwrap(superpixel_features)
+    as_numpy = not isinstance(sp, (torch.Tensor, BatchState)) if st is None else \
+        not isinstance(feats, torch.Tensor)
+    if st is None:
+        dev = _device() if as_numpy else sp.device
+        ent = _CACHE.get('state')
+        if ent is not None and ent[1]() is sp and ent[0] == _fingerprint(sp):
+            st = ent[2]          # labels are already on the device
+    if st is not None:
+        labels, dev = st.raw_labels, st.raw_labels.device
+    else:
+        labels = _labels_to_dev(sp, dev)
+        if labels.dim() == 2:
+            labels = labels[None]
+    # descriptors: the float64 host array we handed out (unchanged) -> its device original
+    if st is not None and st.feat is not None and isinstance(feats, np.ndarray) and \
+            st.feat_token is not None and feats.dtype == np.float64 and \
+            feats.flags.c_contiguous and st.feat_token == _feature_token(feats):
+        feats = st.feat
+    assign = kmeans(k, feats if isinstance(feats, (np.ndarray, torch.Tensor)) else
+                    _to_dev(feats, dev), superpixel_weights, n_iter=n_iter,
                     init_assign=init_assign)
+    if not isinstance(assign, torch.Tensor):
+        assign = torch.from_numpy(np.asarray(assign).astype(np.int32))
     n_per = np.asarray(n_superpixels_per_image, dtype=np.int64)
     sp_off_h = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int64)
     sp_off = torch.from_numpy(sp_off_h).to(dev)

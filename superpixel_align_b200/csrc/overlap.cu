@@ -760,6 +760,13 @@ rowsort_heavy_kernel(OverlapWs ws, const int* __restrict__ indptr, int ncell, in
 //               integer sums (area, sum_y, sum_x) and the float64 prior in sorted order
 //   heavy       rows > 128 cells: dense scatter + ordered compaction
 // ==========================================================================================
+// Where the float64 prior of a pair is evaluated.  1: in emit, L - 1 masked sums per cell of L
+// labels (the last label takes the complement of the whole-cell prior), bucket entries carry the
+// prior.  0: in rowsort from the pixel masks the entries carry (every partial pair pays a
+// masked sum; measured 0.24 ms slower per 300 images).
+#ifndef K1_PRIOR_IN_EMIT
+#define K1_PRIOR_IN_EMIT 1
+#endif
 constexpr int BUCKET_CAP = 128;
 constexpr int TILE_W = 16, TILE_H = 8;  // cells per emit block
 #ifndef EMIT2_MIN_BLOCKS
@@ -883,6 +890,41 @@ __device__ __forceinline__ void place_pair(const S8Ws& ws, int row, const int4& 
   store_pair(ws, row, atomicAdd(&ws.cursor[row], 1), e, spill_cap, nnz_flags);
 }
 
+// Prior mass of one pair from its pixel mask (lo = pixel rows 0..3, hi = rows 4..7, one byte per
+// row): sum_r gy[r] * (sum of gx over the row's set columns), the inner sums looked up in the
+// nibble tables of the cell column.  A whole cell is gy8 * gx8.  Fixed evaluation order.
+struct PriorTabs {
+  const double* gyT;  // [8][fh] (lanes of a warp hold neighbouring cells: one line per load)
+  int fh;
+  const double* gxT;  // [fw][32]
+  const double* gx8;  // [fw]
+  const double* gy8;  // [fh]
+};
+__device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
+                                             unsigned lo, unsigned hi) {
+  if (packed_cnt(packed) == 64) return __dmul_rn(__ldg(pt.gy8 + cyy), __ldg(pt.gx8 + cxx));
+  const double* T = pt.gxT + (size_t)cxx * 32;
+  const double* g = pt.gyT + cyy;
+  double pr = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
+    const double rs = __dadd_rn(__ldg(T + (b & 15u)), __ldg(T + 16 + (b >> 4)));
+    pr = __fma_rn(__ldg(g + (size_t)r * pt.fh), rs, pr);
+  }
+  return pr;
+}
+
+// prior of a bucket entry (c, packed, e2, e3)
+__device__ __forceinline__ double entry_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
+                                              int e2, int e3) {
+#if K1_PRIOR_IN_EMIT
+  return __hiloint2double(e3, e2);
+#else
+  return pair_prior(pt, cyy, cxx, packed, (unsigned)e2, (unsigned)e3);
+#endif
+}
+
 // bit j of the result = (v[j] == L): one compare and one predicated OR per pixel
 __device__ __forceinline__ void mask_or_eq(unsigned& acc, int v, int L, unsigned bit) {
   asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q or.b32 %0, %0, %3; }"
@@ -892,7 +934,11 @@ __device__ __forceinline__ void mask_or_eq(unsigned& acc, int v, int L, unsigned
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if K1_LABELS_L1
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -900,13 +946,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef EMIT_CELLS_PER_THREAD
 #define EMIT_CELLS_PER_THREAD 8
 #endif
+// A/B switches (profiles/README.md, round 2; K1 per 300 images on a B200):
+//   K1_LABELS_L1 1: cp.async.ca -- labels also allocate in L1, the next-label re-read hits L1:
+//                   0.91 ms against 1.15 ms with cp.async.cg + L2 re-read
+//   K1_SYNCWARP / K1_CANDIDATES: reconverging the warp before every cell / looking for the next
+//                   label in fixed register positions first: no measurable difference -> off
+#ifndef K1_LABELS_L1
+#define K1_LABELS_L1 1
+#endif
+#ifndef K1_SYNCWARP
+#define K1_SYNCWARP 0
+#endif
+#ifndef K1_CANDIDATES
+#define K1_CANDIDATES 0
+#endif
 constexpr int EMIT_CELLS = EMIT_CELLS_PER_THREAD;  // cells per thread (16-cell tiles along x)
+
 
 template <typename LabelT>
 __global__ void __launch_bounds__(TILE_W * TILE_H, EMIT2_MIN_BLOCKS)
 emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                  const int64_t* __restrict__ sp_off, S8Ws ws, int64_t spill_cap,
-                 int64_t* nnz_flags) {
+                 int64_t* nnz_flags, PriorTabs pt, bool have_prior) {
   // Software pipeline per thread, no block barrier anywhere: the labels of the NEXT cell travel
   // global -> shared memory with cp.async while the current cell is processed out of registers;
   // the pairs of a cell wait in shared memory until all of them are known, their slot atomics
@@ -942,9 +1003,11 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
 #pragma unroll 1
   for (int it = 0; it < EMIT_CELLS; ++it) {
     const int cx = cx0 + it * TILE_W;
-    // lanes leave the label loop below at different times: without this barrier the warp stays
-    // split into sub-warps for all following cells (measured: 1.7x the instructions)
+    // lanes leave the label loop below at different times and the warp stays split into
+    // sub-warps for the following cells; forcing it back together did not pay (see above)
+#if K1_SYNCWARP
     __syncwarp();
+#endif
     if (cx >= fw) continue;
     const int c = cy * fw + cx;
     const LabelT* p = prow + (size_t)cx * 8;
@@ -964,6 +1027,12 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
     }
     if (it + 1 < EMIT_CELLS && cx + TILE_W < fw) prefetch(cx + TILE_W);
     unsigned long long remaining = ~0ull;
+#if K1_PRIOR_IN_EMIT
+    const double cell_prior =
+        have_prior ? __dmul_rn(__ldg(pt.gy8 + cy), __ldg(pt.gx8 + cx)) : 0.0;
+    double emitted_prior = 0.0;
+    bool can_complement = true;
+#endif
     int L = v[0];
     int npend_prev = npend;  // pairs of the previous cell whose slot atomics are in flight
     npend = 0;
@@ -988,12 +1057,18 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
     nextl = v[q];                                \
     found = true;                                \
   }
+#if K1_CANDIDATES
       SPALIGN_CAND(63) SPALIGN_CAND(7) SPALIGN_CAND(56) SPALIGN_CAND(36) SPALIGN_CAND(27)
       SPALIGN_CAND(60) SPALIGN_CAND(3) SPALIGN_CAND(39) SPALIGN_CAND(24)
+#endif
 #undef SPALIGN_CAND
       if (remaining != 0ull && !found) {
         const int i = __ffsll((long long)remaining) - 1;
+#if K1_LABELS_L1
+        const LabelT nextq = __ldg(p + (size_t)(i >> 3) * W + (i & 7));
+#else
         const LabelT nextq = __ldcg(p + (size_t)(i >> 3) * W + (i & 7));
+#endif
         nextl = (sizeof(LabelT) == 4) ? (int)nextq
                                       : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
       }
@@ -1015,6 +1090,21 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
                           4 * __popcll(m & 0xffffffff00000000ull);
           packed = cnt | (syl << 7) | (sxl << 15);
         }
+#if K1_PRIOR_IN_EMIT
+        double pr = cell_prior;
+        if (cnt != 64 && have_prior) {
+          if (remaining == 0ull && can_complement) {
+            // last label of the cell: whole-cell prior minus what the other labels took
+            pr = __dadd_rn(cell_prior, -emitted_prior);
+          } else {
+            pr = pair_prior(pt, cy, cx, packed, lo, hi);
+            emitted_prior = __dadd_rn(emitted_prior, pr);
+          }
+        }
+        const int e2 = __double2loint(pr), e3 = __double2hiint(pr);
+#else
+        const int e2 = (int)lo, e3 = (int)hi;
+#endif
         if (npend == PEND) {  // more than PEND labels in one cell: place the oldest now
           const int row = s_prow[0][t];
           const int4 e = s_pend[0][t];
@@ -1027,10 +1117,13 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
           place_pair(ws, row, e, spill_cap, nnz_flags);
         }
         s_prow[npend][t] = (int)(row0 + L);
-        s_pend[npend][t] = make_int4(c, packed, (int)lo, (int)hi);
+        s_pend[npend][t] = make_int4(c, packed, e2, e3);
         ++npend;
       } else {  // label outside [0, n_sp): flag it, emit nothing
         bad = true;
+#if K1_PRIOR_IN_EMIT
+        can_complement = false;
+#endif
       }
       if (remaining == 0ull) break;
       L = nextl;
@@ -1063,31 +1156,6 @@ spill_scatter_kernel(S8Ws ws, const int* __restrict__ indptr, int64_t nnz_cap,
       ws.u_prior[pos] = ws.t_prior[t];
     }
   }
-}
-
-// Prior mass of one pair from its pixel mask (lo = pixel rows 0..3, hi = rows 4..7, one byte per
-// row): sum_r gy[r] * (sum of gx over the row's set columns), the inner sums looked up in the
-// nibble tables of the cell column.  A whole cell is gy8 * gx8.  Fixed evaluation order.
-struct PriorTabs {
-  const double* gyT;  // [8][fh] (lanes of a warp hold neighbouring cells: one line per load)
-  int fh;
-  const double* gxT;  // [fw][32]
-  const double* gx8;  // [fw]
-  const double* gy8;  // [fh]
-};
-__device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
-                                             unsigned lo, unsigned hi) {
-  if (packed_cnt(packed) == 64) return __dmul_rn(__ldg(pt.gy8 + cyy), __ldg(pt.gx8 + cxx));
-  const double* T = pt.gxT + (size_t)cxx * 32;
-  const double* g = pt.gyT + cyy;
-  double pr = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
-    const double rs = __dadd_rn(__ldg(T + (b & 15u)), __ldg(T + 16 + (b >> 4)));
-    pr = __fma_rn(__ldg(g + (size_t)r * pt.fh), rs, pr);
-  }
-  return pr;
 }
 
 // one warp per row of <= BUCKET_CAP cells, straight out of the bucket
@@ -1163,7 +1231,7 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       y_sum = (long long)cn * (cyy * 8) + packed_sy(e.y);
       x_sum = (long long)cn * (cxx * 8) + packed_sx(e.y);
       if (sum_prior != nullptr)
-        ps = __dadd_rn(0.0, pair_prior(pt, cyy, cxx, e.y, (unsigned)e.z, (unsigned)e.w));
+        ps = __dadd_rn(0.0, entry_prior(pt, cyy, cxx, e.y, e.z, e.w));
     }
     if (lane + 32 < L) {
       const int4 e = bk[k1 & 127u];
@@ -1174,7 +1242,7 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       y_sum += (long long)cn * (cyy * 8) + packed_sy(e.y);
       x_sum += (long long)cn * (cxx * 8) + packed_sx(e.y);
       if (sum_prior != nullptr) {
-        pv1 = pair_prior(pt, cyy, cxx, e.y, (unsigned)e.z, (unsigned)e.w);
+        pv1 = entry_prior(pt, cyy, cxx, e.y, e.z, e.w);
         ps = __dadd_rn(ps, pv1);
       }
     }
@@ -1198,7 +1266,7 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
         indices[base + rank] = me.x;
         counts[base + rank] = cn;
         if (sum_prior != nullptr)
-          sorted_prior[base + rank] = pair_prior(pt, cyy, cxx, me.y, (unsigned)me.z, (unsigned)me.w);
+          sorted_prior[base + rank] = entry_prior(pt, cyy, cxx, me.y, me.z, me.w);
         a_sum += cn;
         y_sum += (long long)cn * (cyy * 8) + packed_sy(me.y);
         x_sum += (long long)cn * (cxx * 8) + packed_sx(me.y);
@@ -1275,9 +1343,9 @@ rowsort_heavy_s8_kernel(S8Ws ws, const int* __restrict__ indptr, int ncell, int 
         y_sum += (long long)cn * (cyy * 8) + packed_sy(pk);
         x_sum += (long long)cn * (cxx * 8) + packed_sx(pk);
         if (sum_prior != nullptr) {
-          const double mb = d_prior[c];  // mask bits
-          p_sum = __dadd_rn(p_sum, pair_prior(pt, cyy, cxx, pk, (unsigned)__double2loint(mb),
-                                              (unsigned)__double2hiint(mb)));
+          const double mb = d_prior[c];  // prior, or the mask bits
+          p_sum = __dadd_rn(p_sum, entry_prior(pt, cyy, cxx, pk, __double2loint(mb),
+                                               __double2hiint(mb)));
         }
       }
       running += total;
@@ -1403,18 +1471,19 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
     dim3 egrid((fw + TILE_W * EMIT_CELLS - 1) / (TILE_W * EMIT_CELLS), (fh + TILE_H - 1) / TILE_H,
                n_img);
     constexpr int NT = TILE_W * TILE_H;
+    const PriorTabs pt{w8.gyT, fh, w8.gxT, w8.gx8, w8.gy8};
     if (label_dtype == SPALIGN_I32) {
       const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4);
       SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int32_t>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       emit_s8v2_kernel<int32_t><<<egrid, NT, smem, stream>>>(
-          (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags);
+          (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
     } else {
       const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4);
       SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int64_t>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       emit_s8v2_kernel<int64_t><<<egrid, NT, smem, stream>>>(
-          (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags);
+          (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
     }
     const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
     scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum);
@@ -1423,7 +1492,6 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
                                                     w8.heavy_count, w8.heavy_cap, nullptr, 0,
                                                     BUCKET_CAP);
     spill_scatter_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, indptr, nnz_cap, nnz_flags);
-    const PriorTabs pt{w8.gyT, fh, w8.gxT, w8.gx8, w8.gy8};
     rowsort_bucket_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(
         w8, indptr, n_rows, fw, indices, counts, area, sum_y, sum_x, sum_prior, nnz_flags, ncell,
         pt);

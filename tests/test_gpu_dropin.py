@@ -233,3 +233,110 @@ def test_superpixel_align_dropin_bilinear_mode(batch):
     want = so.pool_dense_bilinear(labs[0], feats[0])
     assert got.dtype == np.float32
     np.testing.assert_allclose(got, want.astype(np.float32), rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------- inline reference code, frozen (round 2)
+def test_refine_dropin_reference_inline_golden(golden_dir):
+    """CUDA K1 counts + K5 refine + K4 paint against the reference's own refine loop
+    (superpixel_overlaps.py:360-369, run unmodified by oracle/gen_golden.py)."""
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    from superpixel_align_b200 import superpixel_overlaps as spo
+    g = np.load(os.path.join(golden_dir, 'refine_ref.npz'))
+    for name in ('s8', 'ratio', 'r224'):
+        lab, road = g[name + '__label'], g[name + '__road_cell']
+        for thr in (0.01, 0.05, 0.2):
+            bsk.clear_cache()
+            got = spo.refine_road_masks(lab[None], road[None], thr)
+            assert np.array_equal(got[0], g['%s__refined_%g' % (name, thr)]), (name, thr)
+    got = spo.refine_road_masks(g['noroad__label'][None], np.zeros((1, 8, 12), bool), 0.01)
+    assert not got.any()
+
+
+def test_direct_clustering_dropin_reference_inline_golden(golden_dir):
+    from superpixel_align_b200 import direct_clustering as dc
+    g = np.load(os.path.join(golden_dir, 'direct_features_ref.npz'))
+    n, h, w = int(g['n']), int(g['h']), int(g['w'])
+    # virtual (x, y) columns in the kernel == the matrix the reference materialises (:298-303)
+    got = dc.cluster_cells(g['feats'], g['prior'], 4, init_assign=g['init'])
+    assert np.array_equal(got.reshape(-1), g['assign'])
+    # and the materialised matrix through the reference-named entry point
+    got2 = dc.kmeans(4, g['X'], g['prior'], init_assign=g['init'])
+    assert np.array_equal(np.asarray(got2).astype(np.int32), g['assign'])
+    args = _args()
+    res, road = dc.estimate_road_mask(g['feats'], args)      # seeded init drawn inside
+    assert res.shape == (n, h, w) and road.dtype == bool
+
+
+def test_gapped_label_ids_follow_the_reference(golden_dir):
+    """1-based ids with a missing id: rows = sorted unique ids, paint-back by enumerate index."""
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    g = np.load(os.path.join(golden_dir, 'gapped_ref.npz'))
+    labs, n_per = g['labs'], [int(v) for v in g['n_per']]
+    args = _args(n_clusters=int(g['k']))
+    bsk.clear_cache()
+    w = bsk.batch_create_prior(args, labs)
+    np.testing.assert_allclose(w, g['weights'], rtol=1e-12)
+    feats = np.zeros((2, 6, 4, 8), dtype=np.float32)
+    f, got_n = bsk.batch_superpixel_align(args, None, None, labs, feats)
+    assert got_n == n_per and f.shape == (sum(n_per), 8)
+    cres, road = bsk.weighted_kmeans(labs, g['feats'], g['weights'], int(g['k']), n_per,
+                                     init_assign=g['init'])
+    assert np.array_equal(cres, g['cluster_map']) and np.array_equal(road, g['road'])
+
+
+def test_state_cache_never_returns_a_stale_batch(batch):
+    """A preallocated buffer refilled in place (NumPy ``buf[:] = ...``, torch ``copy_``) must not
+    be mistaken for the previous batch; lists are never cached; the explicit handle works."""
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    labs, feats, imgs = batch
+    args = _args()
+    other = np.stack([synth.voronoi_labels(128, 256, 6, 10, image_index=50 + i, dtype=np.int64)
+                      for i in range(3)])
+    want_a = np.concatenate([so.create_prior(l, 0.75, 0.5, 0.1, 0.1) for l in labs])
+    want_b = np.concatenate([so.create_prior(l, 0.75, 0.5, 0.1, 0.1) for l in other])
+    bsk.clear_cache()
+    buf = labs.copy()
+    np.testing.assert_allclose(bsk.batch_create_prior(args, buf), want_a, rtol=1e-12)
+    buf[:] = other                                   # same address, same shape, new content
+    np.testing.assert_allclose(bsk.batch_create_prior(args, buf), want_b, rtol=1e-12)
+    d = torch.device('cuda', 0)
+    tb = torch.from_numpy(labs).to(d)
+    np.testing.assert_allclose(bsk.batch_create_prior(args, tb).cpu().numpy(), want_a, rtol=1e-12)
+    tb.copy_(torch.from_numpy(other))
+    np.testing.assert_allclose(bsk.batch_create_prior(args, tb).cpu().numpy(), want_b, rtol=1e-12)
+    np.testing.assert_allclose(bsk.batch_create_prior(args, [l for l in labs]), want_a, rtol=1e-12)
+    np.testing.assert_allclose(bsk.batch_create_prior(args, [l for l in other]), want_b, rtol=1e-12)
+    # explicit handle: same results as the array route, labels uploaded once
+    st = bsk.prepare_batch(args, labs, feature_shape=feats.shape[-2:])
+    f1, n1 = bsk.batch_superpixel_align(args, None, imgs, st, feats)
+    w1 = bsk.batch_create_prior(args, st)
+    np.random.seed(1111)
+    c1, r1 = bsk.batch_weighted_kmeans(args, st, f1, w1, n1)
+    bsk.clear_cache()
+    f2, n2 = bsk.batch_superpixel_align(args, None, imgs, labs, feats)
+    w2 = bsk.batch_create_prior(args, labs)
+    np.random.seed(1111)
+    c2, r2 = bsk.batch_weighted_kmeans(args, labs, f2, w2, n2)
+    assert n1 == n2 and np.array_equal(f1, f2) and np.array_equal(w1.cpu().numpy(), w2)
+    assert np.array_equal(c1, c2) and np.array_equal(r1, r2)
+    # a caller that edits the descriptors in place gets them clustered, not the cached ones
+    f3 = f2.copy()
+    f3[:, :-2] *= -1.0
+    np.random.seed(1111)
+    c3, _ = bsk.batch_weighted_kmeans(args, labs, f3, w2, n2)
+    np.random.seed(1111)
+    oa = so.kmeans(4, f3, w2, verbose=False)
+    ocm, _ = so.weighted_kmeans_paint(labs, oa, n2)
+    assert np.array_equal(c3, ocm)
+
+
+def test_dropin_centroid_columns_are_exact_float64(batch):
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    labs, feats, imgs = batch
+    bsk.clear_cache()
+    f, n_per = bsk.batch_superpixel_align(_args(), None, imgs, labs, feats)
+    off = 0
+    for i, n in enumerate(n_per):
+        area, sy, sx = so.superpixel_stats(labs[i], n)
+        assert np.array_equal(f[off:off + n, -2], sy / area) and np.array_equal(f[off:off + n, -1], sx / area)
+        off += n

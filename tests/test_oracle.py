@@ -174,3 +174,66 @@ def test_resize_bilinear_matches_torch_align_corners():
     want = torch.nn.functional.interpolate(torch.from_numpy(F)[None], size=(50, 70), mode='bilinear',
                                            align_corners=True)[0].numpy()
     np.testing.assert_allclose(so.resize_bilinear(F, 50, 70), want, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------ inline reference code (refine, direct build)
+def test_refine_matches_reference_inline_loop_golden(golden_dir):
+    """refine_ref.npz = the reference's own loop (superpixel_overlaps.py:360-369) run unmodified:
+    both oracle formulations (CSR row-dot and mask loop) must reproduce it bit for bit."""
+    g = np.load(os.path.join(golden_dir, 'refine_ref.npz'))
+    for name in ('s8', 'ratio', 'r224'):
+        lab, road = g[name + '__label'], g[name + '__road_cell']
+        fh, fw = int(g[name + '__fh']), int(g[name + '__fw'])
+        H, W = lab.shape
+        ip, ix, ct = so.overlap_csr(lab, fh, fw)
+        for thr in (0.01, 0.05, 0.2):
+            want = g['%s__refined_%g' % (name, thr)]
+            _, _, keep = so.refine_overlaps_csr(ip, ix, ct, road, thr)
+            assert np.array_equal(keep[lab].astype(np.uint8), want), (name, thr)
+            assert np.array_equal(so.refine_overlaps_masks(lab, so.upsample_nearest(road, H, W), thr),
+                                  want), (name, thr)
+    lab = g['noroad__label']
+    ip, ix, ct = so.overlap_csr(lab, 8, 12)
+    _, px, keep = so.refine_overlaps_csr(ip, ix, ct, np.zeros((8, 12), bool), 0.01)
+    assert px == 0 and not keep.any() and not g['noroad__refined'].any()
+
+
+def test_direct_feature_build_matches_reference_inline_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'direct_features_ref.npz'))
+    X = so.direct_features(g['feats'])
+    assert X.dtype == g['X'].dtype and np.array_equal(X, g['X'])
+    h, w, n = int(g['h']), int(g['w']), int(g['n'])
+    prior = so.create_prior_map(h, w, 0.75, 0.5, 0.1, 0.1).reshape(1, -1).repeat(n, axis=0).reshape(-1)
+    assert np.array_equal(prior, g['prior'])
+    got = so.kmeans(4, X, prior, init_assign=g['init'].astype(np.float64), verbose=False)
+    assert np.array_equal(np.asarray(got).astype(np.int32), g['assign'])
+
+
+def test_gapped_labels_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'gapped_ref.npz'))
+    labs, n_per = g['labs'], list(g['n_per'])
+    w = np.concatenate([so.create_prior(l, 0.75, 0.5, 0.1, 0.1) for l in labs])
+    np.testing.assert_allclose(w, g['weights'], rtol=1e-13)
+    assign = so.kmeans(int(g['k']), g['feats'], g['weights'], init_assign=g['init'].astype(np.float64),
+                       verbose=False)
+    cmap, road = so.weighted_kmeans_paint(labs, assign, n_per)
+    assert np.array_equal(cmap, g['cluster_map']) and np.array_equal(road, g['road'])
+
+
+@pytest.mark.needs_reference
+def test_inline_reference_code_live():
+    """The golden files above regenerate from the live reference (statement nodes taken from
+    the parsed source by line range; a drifted range raises)."""
+    import types
+    f = ref_extract.refine_loop()
+    lab = synth.voronoi_labels(40, 56, 3, 4, image_index=5)
+    road = np.random.RandomState(1).rand(5, 7) < 0.4
+    (ref,) = f(road.copy(), lab, types.SimpleNamespace(overlap_threshold=0.03))
+    assert np.array_equal(np.asarray(ref, np.uint8),
+                          so.refine_overlaps_masks(lab, so.upsample_nearest(road, 40, 56), 0.03))
+    feats = np.stack([synth.smooth_features(5, 4, 6, seed=i, radius=1) for i in range(3)])
+    X, n, h, w = ref_extract.direct_feature_build()([feats], np)
+    assert (n, h, w) == (3, 4, 6) and np.array_equal(X, so.direct_features(feats))
+    with pytest.raises(ValueError):
+        ref_extract.load_inline('superpixel_overlaps.py', 'estimate_road_mask', 361, 369, 'f',
+                                ['road_mask', 'superpixel', 'args'], ['refined_roadmap'])
