@@ -277,8 +277,9 @@ int spalign_kmeans_debug_stats(int64_t* out_host, int reset);
  * thr = sort(w_g)[N_g/2]; rows with w > thr -> 0; the others take shuffled[g_shuf_off + i]
  * in row order.  `shuffled` holds, per group, arange(m) % (K-1) + 1 already shuffled by the
  * host with the NumPy legacy stream for the expected m = N_g/2 + 1; status_m[g] receives
- * the actual m so the host can detect a tie-induced mismatch (-1: group larger than the
- * 4096-row shared-memory sort, initialise on the host instead). */
+ * the actual m so the host can detect a tie-induced mismatch.  Groups of up to 4096 rows sort
+ * their weights in shared memory; larger ones (joint clustering of 30 images, cell clustering)
+ * find the median with an 8-pass radix select over global memory -- any group size. */
 int spalign_kmeans_init(const double* w, const int64_t* group_off, int G,
                         const int32_t* shuffled, const int64_t* shuf_off, int32_t* assign,
                         int32_t* m_out, spalign_stream_t stream);

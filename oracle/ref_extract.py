@@ -5,9 +5,10 @@ not installed), but the functions on the hot path are written against ``xp`` and
 NumPy unchanged.  This module parses a reference file with ``ast``, keeps only the wanted
 ``FunctionDef`` nodes and ``exec``s them in a namespace with a three-symbol shim
 (SURVEY.md section 8c).  Nothing is copied into the repo: the source is read from
-``/root/reference`` at call time, so this only works in the authoring container.  It is
-used by ``oracle/gen_golden.py`` (to freeze golden vectors) and by the
-``needs_reference`` tests (skipped where ``/root/reference`` is absent, e.g. the GPU box).
+``/root/reference`` at call time (authoring container) or, on the GPU box, from the copies
+``oracle/make_ref.py`` leaves under the git-ignored ``oracle/_ref/``.  It is used by
+``oracle/gen_golden.py`` (to freeze golden vectors), by the ``needs_reference`` tests and by
+``bench.py``'s CPU baseline of kind "reference".
 """
 from __future__ import annotations
 
@@ -19,7 +20,21 @@ import warnings
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('SPALIGN_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _root() -> str:
+    """/root/reference where it exists (authoring container), else the copies that
+    oracle/make_ref.py left under oracle/_ref/ (they travel to the GPU box with gpurun)."""
+    env = os.environ.get('SPALIGN_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isfile('/root/reference/batch_spalign_kmeans.py'):
+        return '/root/reference'
+    return os.path.join(_HERE, '_ref')
+
+
+REFERENCE_ROOT = _root()
 
 _WANTED = {
     'batch_spalign_kmeans.py': {

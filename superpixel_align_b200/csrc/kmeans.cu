@@ -1969,8 +1969,15 @@ kmeans_update_kernel(const double* __restrict__ totals, int D, int K, int mode, 
                   iters, status, grp);
 }
 
-// seeded init for small groups: upper median by bitonic sort in shared memory
+// seeded init: upper median of the group's weights -- bitonic sort in shared memory up to
+// INIT_MAX rows, an 8-pass radix select over the rows in global memory beyond that (joint
+// clustering of 30 images = 30 000 rows, direct cell clustering) -- then the rows at or below it
+// take the host-shuffled cluster ids in row order
 constexpr int INIT_MAX = 4096;
+__device__ __forceinline__ unsigned long long f64_order_key(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);  // ascending keys == ascending doubles
+}
 __global__ void __launch_bounds__(256)
 kmeans_init_kernel(const double* __restrict__ w, const int64_t* __restrict__ group_off,
                    const int32_t* __restrict__ shuffled, const int64_t* __restrict__ shuf_off,
@@ -1978,38 +1985,73 @@ kmeans_init_kernel(const double* __restrict__ w, const int64_t* __restrict__ gro
   __shared__ double key[INIT_MAX];
   const int grp = blockIdx.x;
   const int64_t r0 = group_off[grp];
-  const int n = (int)(group_off[grp + 1] - r0);
+  const int64_t n64 = group_off[grp + 1] - r0;
   const int t = threadIdx.x;
-  if (n <= 0) {
+  if (n64 <= 0) {
     if (t == 0) m_out[grp] = 0;
     return;
   }
-  int p2 = 1;
-  while (p2 < n) p2 <<= 1;
-  if (p2 > INIT_MAX) {  // too large for the shared-memory sort: the host initialises instead
+  if (n64 > 0x7fffffffLL) {  // not a size this path is meant for
     if (t == 0) m_out[grp] = -1;
     return;
   }
-  for (int i = t; i < p2; i += 256) key[i] = i < n ? w[r0 + i] : __longlong_as_double(0x7ff0000000000000LL);
-  __syncthreads();
-  for (int k = 2; k <= p2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = t; i < p2; i += 256) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const double a = key[i], b = key[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            key[i] = b;
-            key[ixj] = a;
+  const int n = (int)n64;
+  int p2 = 1;
+  while (p2 < n) p2 <<= 1;
+  double thr;
+  if (p2 <= INIT_MAX) {
+    for (int i = t; i < p2; i += 256)
+      key[i] = i < n ? w[r0 + i] : __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = t; i < p2; i += 256) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const double a = key[i], b = key[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              key[i] = b;
+              key[ixj] = a;
+            }
           }
         }
+        __syncthreads();
+      }
+    }
+    thr = key[n / 2];
+    __syncthreads();
+  } else {
+    // radix select of the element of rank n/2 (ascending), most significant byte first
+    int* hist = reinterpret_cast<int*>(key);
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_rank;
+    if (t == 0) {
+      s_prefix = 0ull;
+      s_rank = n / 2;
+    }
+    for (int pass = 7; pass >= 0; --pass) {
+      hist[t] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = t; i < n; i += 256) {
+        const unsigned long long k = f64_order_key(w[r0 + i]);
+        if (pass == 7 || (k >> (8 * (pass + 1))) == prefix)
+          atomicAdd(&hist[(int)((k >> (8 * pass)) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (t == 0) {
+        int rank = s_rank, b = 0;
+        while (b < 255 && rank >= hist[b]) rank -= hist[b++];
+        s_rank = rank;
+        s_prefix = (prefix << 8) | (unsigned long long)b;
       }
       __syncthreads();
     }
+    const unsigned long long k = s_prefix;
+    thr = __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+    __syncthreads();
   }
-  const double thr = key[n / 2];
-  __syncthreads();
   const int64_t s0 = shuf_off[grp];
   const int m_exp = (int)(shuf_off[grp + 1] - s0);
   // ordered rank of rows with w <= thr (reference: assign[cond] = idx)

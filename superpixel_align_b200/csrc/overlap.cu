@@ -560,13 +560,23 @@ scatter_kernel(OverlapWs ws, int cap_img, const int* __restrict__ indptr, int64_
 
 // one warp per row with <= WARP_TIER_MAX cells: rank sort by cell id
 __global__ void __launch_bounds__(256)
-rowsort_warp_kernel(OverlapWs ws, const int* __restrict__ indptr, int64_t R, int* indices,
+rowsort_warp_kernel(OverlapWs ws, int* indptr, int64_t R, int* indices,
                     int* counts, int* area, double* sum_prior, double* wvals,
                     const int64_t* __restrict__ nnz_flags, int ncell_hint) {
-  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) return;
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
   const int lane = lane_id();
+  if (nnz_flags[1] & SPALIGN_F_NNZ_OVERFLOW) {
+    // capacity exceeded: leave an EMPTY matrix behind (no row reaches into unwritten storage),
+    // the flag tells the caller
+    if (lane == 0) {
+      indptr[r] = 0;
+      if (r == R - 1) indptr[R] = 0;
+      area[r] = 0;
+      if (sum_prior != nullptr) sum_prior[r] = 0.0;
+    }
+    return;
+  }
   const int base = indptr[r];
   const int L = indptr[r + 1] - base;
   if (L > WARP_TIER_MAX) return;

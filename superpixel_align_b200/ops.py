@@ -637,9 +637,9 @@ def kmeans_debug_stats(reset: bool = False):
 
 def kmeans_init_device(w: torch.Tensor, group_off: torch.Tensor, shuffled: torch.Tensor,
                        shuf_off: torch.Tensor):
-    """Seeded init on the device for groups of <= 4096 rows.  Returns (assign int32 [N],
-    m int32 [G]); m[g] != len(shuffled_g) means prior-weight ties changed the split size and
-    the host must redo that group's init (m[g] == -1: group too large)."""
+    """Seeded init on the device (any group size).  Returns (assign int32 [N], m int32 [G]);
+    m[g] != len(shuffled_g) means prior-weight ties changed the split size: the shuffle drawn
+    for the expected size does not match the reference's stream for that group."""
     _require_cuda(w, group_off, shuffled, shuf_off)
     G = group_off.numel() - 1
     assign = torch.empty(w.numel(), dtype=torch.int32, device=w.device)

@@ -33,6 +33,22 @@ class PipelineOutput:
     group_off_host: np.ndarray
     shuf_sizes: np.ndarray
 
+    def check(self):
+        """Synchronises.  Raises on an overflowed / out-of-range overlap matrix (whose rows were
+        then left EMPTY by K1, so nothing downstream read unwritten storage) and on label ids
+        with gaps; returns the number of groups whose prior weights were tied at the median, for
+        which the seeded init differs from the reference's ``np.random`` stream."""
+        self.overlap.validate()
+        if self.overlap.has_empty_rows:
+            raise ValueError('label ids are not contiguous 0..S-1 (rows without pixels): use '
+                             'batch_spalign_kmeans.prepare_batch, which relabels like the reference')
+        ties = int((self.init_m.cpu().numpy() != np.asarray(self.shuf_sizes)).sum())
+        if ties:
+            import warnings
+            warnings.warn('%d group(s) with prior weights tied at the median: their seeded init '
+                          'does not follow the reference stream' % ties)
+        return ties
+
 
 def draw_shuffles(k: int, group_sizes: Sequence[int]):
     """Host side of the seeded init (batch_spalign_kmeans.py:146-148): for every group, in
@@ -58,8 +74,10 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
               out=None) -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
-    1 = per-image clustering).  Groups of more than 4096 rows use the host-driven multi-CTA
-    k-means (which polls a stop flag); everything else is sync-free."""
+    1 = per-image clustering).  Groups of more than 2048 rows use the multi-CTA k-means whose
+    driver polls a stop flag asynchronously; everything else is free of host synchronisation.
+    Data-dependent conditions (overlap capacity, label range, empty rows, tied prior weights)
+    are left in device words: call ``.check()`` on the result at the next synchronisation."""
     n = labels.shape[0]
     n_sp = np.asarray(n_sp, dtype=np.int64)
 
@@ -87,41 +105,20 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
     group_off_host = ov.sp_off_host[g_idx]
     sizes = np.diff(group_off_host)
     dev = labels.device
-    if sizes.max() <= 4096:
-        flat, off, m_exp = draw_shuffles(k, sizes)
-        goff = ov.sp_off if images_per_group == 1 else \
-            torch.from_numpy(group_off_host).to(dev, non_blocking=True)
-        flat_d = torch.from_numpy(flat).to(dev, non_blocking=True)
-        off_d = torch.from_numpy(off).to(dev, non_blocking=True)
-        mark('init', True)
-        init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
-        mark('init', False)
-        mark('kmeans', True)
-        if kmeans_impl == 'groups':
-            res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
-        else:  # many CTAs per image, finished images dropped as the iterations go on
-            res = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter).run()
-        mark('kmeans', False)
-    else:
-        # large joint groups: the median split needs a sort of N doubles -> host init
-        w_host = weights.cpu().numpy()
-        init_host = np.zeros(len(w_host), dtype=np.int32)
-        m_list = []
-        for g in range(len(sizes)):
-            a, b = group_off_host[g], group_off_host[g + 1]
-            wg = w_host[a:b]
-            thr = float(np.sort(wg)[len(wg) // 2])
-            low = wg <= thr
-            idx = np.arange(int(low.sum())) % (k - 1) + 1
-            np.random.shuffle(idx)
-            init_host[a:b][low] = idx
-            m_list.append(int(low.sum()))
-        m = torch.tensor(m_list, dtype=torch.int32)
-        m_exp = np.asarray(m_list)
-        mark('kmeans', True)
-        res = ops.KMeansLarge(feats, weights, torch.from_numpy(init_host).to(dev), k,
-                              group_off_host, n_iter=n_iter).run()
-        mark('kmeans', False)
+    flat, off, m_exp = draw_shuffles(k, sizes)
+    goff = ov.sp_off if images_per_group == 1 else \
+        torch.from_numpy(group_off_host).to(dev, non_blocking=True)
+    flat_d = torch.from_numpy(flat).to(dev, non_blocking=True)
+    off_d = torch.from_numpy(off).to(dev, non_blocking=True)
+    mark('init', True)
+    init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
+    mark('init', False)
+    mark('kmeans', True)
+    if kmeans_impl == 'groups':
+        res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
+    else:  # many CTAs per group; small groups finish in one persistent CTA each
+        res = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter).run()
+    mark('kmeans', False)
     mark('paint', True)
     cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype, out=out)
     mark('paint', False)
@@ -270,6 +267,150 @@ class HostPipeline:
                 ev_c.record(self.comp)
             comp_done[s] = ev_c
             if pending is not None:      # hand the previous result to the caller
+                pi, ps, pb, pev = pending
+                pev.synchronize()
+                if on_result is not None:
+                    on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_event(ev_c)
+                self.out_c[s][:b].copy_(out.cluster_map, non_blocking=True)
+                self.out_m[s][:b].copy_(out.road_mask, non_blocking=True)
+                ev_d = torch.cuda.Event()
+                ev_d.record(self.copy)
+            out.cluster_map.record_stream(self.copy)
+            out.road_mask.record_stream(self.copy)
+            self.d2h_bytes += 2 * b * H * W
+            pending = (i, s, b, ev_d)
+            up = nxt
+        pi, ps, pb, pev = pending
+        pev.synchronize()
+        if on_result is not None:
+            on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process (and with it the first-touch placement of the pinned pools it allocates
+    next) to the CPUs NVML reports as local to the GPU.  On hosts that expose a single NUMA node
+    this changes nothing; it is the software half of keeping eight host->device streams from
+    meeting on one memory controller.  Returns what was done, for the bench record."""
+    import os
+    info = {'device': int(device_index), 'bound': False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c < n_cpu]
+        try:
+            info['numa_node'] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, n_cpus=len(allowed), cpu_first=allowed[0], cpu_last=allowed[-1])
+    except Exception as e:  # pragma: no cover
+        info['error'] = repr(e)[:120]
+    return info
+
+
+class ImagePipeline:
+    """The reference's real boundary (estimate_road_mask, batch_spalign_kmeans.py:427-457) for
+    inputs in HOST memory: uint8 RGB images [b, 3, H, W] and label maps [b, H, W] (uint16 when
+    S <= 65535, else int32) go host -> device, the DRN backbone (PyTorch / cuDNN, the input
+    producer) runs on the device, its stride-8 map feeds K1..K4 without ever leaving HBM, and the
+    uint8 cluster maps / road masks come back.  Copies run on a second stream, double buffered.
+
+        ip = ImagePipeline(model, H, W, sub_batch=4)
+        ip.process([(images_u8_cpu, labels_cpu, n_sp), ...], on_result=lambda i, cmap, mask: ...)
+    """
+
+    MEAN = (0.485, 0.456, 0.406)
+    STD = (0.229, 0.224, 0.225)
+
+    def __init__(self, model, H, W, sub_batch=4, k=4, prior=(0.75, 0.5, 0.1, 0.1), append_pos=True,
+                 device=None, label_dtype=torch.int16, backbone_dtype=torch.float32):
+        self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.model, self.H, self.W, self.B = model, H, W, sub_batch
+        self.k, self.prior, self.append_pos = k, prior, append_pos
+        self.backbone_dtype = backbone_dtype
+        d = self.dev
+        self.img = [torch.empty((sub_batch, 3, H, W), dtype=torch.uint8, device=d) for _ in range(2)]
+        self.lab = [torch.empty((sub_batch, H, W), dtype=label_dtype, device=d) for _ in range(2)]
+        self.out_c = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.out_m = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.copy = torch.cuda.Stream(device=d)
+        self.comp = torch.cuda.Stream(device=d)
+        self.mean = torch.tensor(self.MEAN, device=d).view(1, 3, 1, 1) * 255.0
+        self.istd = 1.0 / (torch.tensor(self.STD, device=d).view(1, 3, 1, 1) * 255.0)
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.backbone_ms = []        # (event, event) pairs around the backbone, read by the bench
+
+    def _upload(self, slot, imgs_cpu, labels_cpu, free_event):
+        b = imgs_cpu.shape[0]
+        with torch.cuda.stream(self.copy):
+            if free_event is not None:
+                self.copy.wait_event(free_event)
+            self.img[slot][:b].copy_(imgs_cpu, non_blocking=True)
+            self.lab[slot][:b].copy_(labels_cpu, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        self.h2d_bytes += imgs_cpu.numel() * imgs_cpu.element_size() + \
+            labels_cpu.numel() * labels_cpu.element_size()
+        return ev
+
+    def features(self, imgs_u8):
+        """uint8 [b,3,H,W] on the device -> cell-major float32 [b, fh*fw, C] (layer8 of the DRN,
+        normalised like models/drn.py:304-325)."""
+        with torch.no_grad():
+            x = (imgs_u8.float() - self.mean) * self.istd
+            x = x.contiguous(memory_format=torch.channels_last)
+            if self.backbone_dtype != torch.float32:
+                with torch.autocast('cuda', dtype=self.backbone_dtype):
+                    f = self.model(x)
+            else:
+                f = self.model(x)
+            f = f.float().contiguous(memory_format=torch.channels_last)
+        n, C, fh, fw = f.shape
+        return f.permute(0, 2, 3, 1).reshape(n, fh * fw, C), fh, fw
+
+    def process(self, batches, on_result=None, time_backbone=False):
+        batches = list(batches)
+        n = len(batches)
+        if n == 0:
+            return
+        H, W = self.H, self.W
+        comp_done = [None, None]
+        up = self._upload(0, batches[0][0], batches[0][1], None)
+        pending = None
+        for i in range(n):
+            s = i & 1
+            imgs_cpu, labels_cpu, n_sp = batches[i]
+            b = imgs_cpu.shape[0]
+            nxt = None
+            if i + 1 < n:
+                nxt = self._upload(s ^ 1, batches[i + 1][0], batches[i + 1][1], comp_done[s ^ 1])
+            with torch.cuda.stream(self.comp):
+                self.comp.wait_event(up)
+                if time_backbone:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record(self.comp)
+                feat, fh, fw = self.features(self.img[s][:b])
+                if time_backbone:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record(self.comp)
+                    self.backbone_ms.append((e0, e1, b))
+                labels = self.lab[s][:b].to(torch.int32)     # uint16 on the wire, int32 for K1/K4
+                if self.lab[s].dtype == torch.int16:
+                    labels = labels & 0xffff
+                out = run_batch(labels, feat, n_sp, fh, fw, k=self.k, prior=self.prior,
+                                append_pos=self.append_pos)
+                ev_c = torch.cuda.Event()
+                ev_c.record(self.comp)
+            comp_done[s] = ev_c
+            if pending is not None:
                 pi, ps, pb, pev = pending
                 pev.synchronize()
                 if on_result is not None:

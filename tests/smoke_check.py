@@ -1,5 +1,6 @@
 """smoke(): one small invocation of the hot path on cuda:0, checked against the CPU oracle.
-(The oracle is test infrastructure; this is one of the few places allowed to import it.)"""
+Lives under tests/ (not in the product package) because it imports the oracle, which is test
+infrastructure; __graft_entry__.smoke() is its only caller."""
 from __future__ import annotations
 
 import numpy as np
@@ -8,7 +9,7 @@ import torch
 
 def run_smoke(H=256, W=512, C=64, gy=8, gx=12, k=4, verbose=True):
     from oracle import spalign_oracle as so
-    from . import _lib, ops, pipeline, synth
+    from superpixel_align_b200 import _lib, ops, pipeline, synth
     _lib.load()
     assert torch.cuda.is_available(), 'smoke() needs a CUDA device'
     dev = torch.device('cuda', 0)

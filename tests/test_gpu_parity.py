@@ -144,6 +144,27 @@ def test_overlap_capacity_overflow_is_flagged(ops):
         ov.validate()
 
 
+def test_pipeline_overflow_leaves_empty_matrix_and_is_reported(ops):
+    # the sync-free pipeline never reads the flags: on overflow K1 must leave an EMPTY matrix so
+    # that pooling / k-means / paint stay inside their buffers, and check() reports it
+    from superpixel_align_b200 import pipeline
+    for H, W, fh, fw in ((64, 128, 8, 16), (50, 70, 7, 9)):          # stride-8 and generic K1
+        lab = np.stack([synth.noise_labels(H, W, 50, seed=s) for s in (3, 4)])
+        feats = torch.randn((2, fh * fw, 16), device=dev())
+        out = pipeline.run_batch(torch.from_numpy(lab).to(dev()), feats, [50, 50], fh, fw,
+                                 nnz_cap_per_image=100)
+        torch.cuda.synchronize()
+        assert int(out.overlap.indptr.abs().sum().item()) == 0
+        assert int(out.overlap.area.abs().sum().item()) == 0
+        with pytest.raises(OverflowError):
+            out.check()
+    lab = np.stack([synth.voronoi_labels(64, 128, 4, 8, image_index=i) for i in range(2)])
+    feats = torch.randn((2, 8 * 16, 16), device=dev())
+    np.random.seed(3)
+    out = pipeline.run_batch(torch.from_numpy(lab).to(dev()), feats, [32, 32], 8, 16)
+    assert out.check() == 0
+
+
 def test_label_max(ops):
     labs = np.stack([synth.voronoi_labels(40, 50, 3, 4, image_index=i) for i in range(3)])
     labs[1] = labs[1] % 7
@@ -382,7 +403,7 @@ def test_kmeans_large_many_groups_and_chunks(ops):
 
 def test_kmeans_init_device_matches_host(ops):
     rs = np.random.RandomState(9)
-    sizes = [1000, 37, 2, 1, 4096, 513]
+    sizes = [1000, 37, 2, 1, 4096, 513, 4097, 30000, 70001]   # > 4096: radix-select median
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     w = rs.uniform(0, 1, off[-1])
     from superpixel_align_b200 import pipeline
