@@ -911,7 +911,7 @@ struct PriorTabs {
   const double* gy8;  // [fh]
 };
 __device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
-                                             unsigned lo, unsigned hi) {
+                                             unsigned lo, unsigned hi) {  // (K1_PRIOR_IN_EMIT 0)
   if (packed_cnt(packed) == 64) return __dmul_rn(__ldg(pt.gy8 + cyy), __ldg(pt.gx8 + cxx));
   const double* T = pt.gxT + (size_t)cxx * 32;
   const double* g = pt.gyT + cyy;
@@ -956,9 +956,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef EMIT_CELLS_PER_THREAD
 #define EMIT_CELLS_PER_THREAD 8
 #endif
-// A/B switches (profiles/README.md, round 2; K1 per 300 images on a B200):
+// A/B switches (profiles/README.md, round 2; K1 per 300 DISTINCT label maps on a B200):
 //   K1_LABELS_L1 1: cp.async.ca -- labels also allocate in L1, the next-label re-read hits L1:
-//                   0.91 ms against 1.15 ms with cp.async.cg + L2 re-read
+//                   0.93-0.98 ms against 1.09-1.11 ms with cp.async.cg + L2 re-read
 //   K1_SYNCWARP / K1_CANDIDATES: reconverging the warp before every cell / looking for the next
 //                   label in fixed register positions first: no measurable difference -> off
 #ifndef K1_LABELS_L1
@@ -989,17 +989,22 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
   int4 (*s_lab)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn);  // [chunk][thread]: conflict-free
   int4 (*s_pend)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn + CH * NT);
   int (*s_prow)[NT] = reinterpret_cast<int (*)[NT]>(s_dyn + (CH + PEND) * NT);
+  // prior tables of the block's 16 cell columns and TILE_H * EMIT_CELLS cell rows: the block walks
+  // DOWN the image, so the column tables (33 doubles per column: 2 x 16 nibble sums + the sum of
+  // all 8) are loaded once; through L1 they competed with the label stream (L2 read traffic 3x
+  // the label bytes, long-scoreboard stalls on every lookup)
+  double (*s_T)[33] = reinterpret_cast<double (*)[33]>(s_dyn + (CH + PEND) * NT + PEND * NT / 4);
+  double* s_gy = reinterpret_cast<double*>(s_T + TILE_W);      // [EMIT_CELLS * TILE_H * 8]
+  double* s_gy8 = s_gy + EMIT_CELLS * TILE_H * 8;              // [EMIT_CELLS * TILE_H]
   const int t = threadIdx.x, tx = t & (TILE_W - 1), ty = t / TILE_W;
   const int img = blockIdx.z;
-  const int cy = blockIdx.y * TILE_H + ty;
-  const int cx0 = blockIdx.x * (TILE_W * EMIT_CELLS) + tx;
-  if (cy >= fh || cx0 >= fw) return;
-  const int64_t row0 = sp_off[img];
-  const int n_sp = (int)(sp_off[img + 1] - row0);
-  const LabelT* prow = labels + ((size_t)img * H + (size_t)cy * 8) * W;
+  const int cx = blockIdx.x * TILE_W + tx;
+  const int cy0 = blockIdx.y * (TILE_H * EMIT_CELLS) + ty;
   constexpr int PER_ROW = 8 * (int)sizeof(LabelT) / 16;  // chunks per pixel row of a cell
-  auto prefetch = [&](int cx) {
-    const char* src = reinterpret_cast<const char*>(prow + (size_t)cx * 8);
+  const LabelT* pcol = labels + (size_t)img * H * W + (size_t)cx * 8;
+  const bool in_x = cx < fw;
+  auto prefetch = [&](int cy) {
+    const char* src = reinterpret_cast<const char*>(pcol + (size_t)cy * 8 * W);
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -1007,20 +1012,42 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
         cp_async16(&s_lab[r * PER_ROW + h][t], src + ((size_t)r * W) * sizeof(LabelT) + h * 16);
     cp_async_commit();
   };
-  prefetch(cx0);
+  if (in_x && cy0 < fh) prefetch(cy0);
+#if K1_PRIOR_IN_EMIT
+  if (have_prior) {
+    for (int e = t; e < TILE_W * 33; e += NT) {
+      const int c = e / 33, k = e - c * 33, gc = blockIdx.x * TILE_W + c;
+      double val = 0.0;
+      if (gc < fw) val = k < 32 ? pt.gxT[(size_t)gc * 32 + k] : pt.gx8[gc];
+      s_T[c][k] = val;
+    }
+    for (int e = t; e < EMIT_CELLS * TILE_H * 8; e += NT) {
+      const int cyy = blockIdx.y * (TILE_H * EMIT_CELLS) + (e >> 3);
+      s_gy[e] = cyy < fh ? pt.gyT[(size_t)(e & 7) * pt.fh + cyy] : 0.0;
+    }
+    for (int e = t; e < EMIT_CELLS * TILE_H; e += NT) {
+      const int cyy = blockIdx.y * (TILE_H * EMIT_CELLS) + e;
+      s_gy8[e] = cyy < fh ? pt.gy8[cyy] : 0.0;
+    }
+  }
+  __syncthreads();   // the only block barrier: tables ready (the first label tile is in flight)
+#endif
+  if (!in_x || cy0 >= fh) return;
+  const int64_t row0 = sp_off[img];
+  const int n_sp = (int)(sp_off[img + 1] - row0);
   int npend = 0, pos[PEND];
   bool bad = false;
 #pragma unroll 1
   for (int it = 0; it < EMIT_CELLS; ++it) {
-    const int cx = cx0 + it * TILE_W;
+    const int cy = cy0 + it * TILE_H;
     // lanes leave the label loop below at different times and the warp stays split into
     // sub-warps for the following cells; forcing it back together did not pay (see above)
 #if K1_SYNCWARP
     __syncwarp();
 #endif
-    if (cx >= fw) continue;
+    if (cy >= fh) break;
     const int c = cy * fw + cx;
-    const LabelT* p = prow + (size_t)cx * 8;
+    const LabelT* p = pcol + (size_t)cy * 8 * W;
     int v[64];
     cp_async_wait_all();
 #pragma unroll
@@ -1035,11 +1062,11 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
         v[2 * k + 1] = (b2 >= 0 && b2 < n_sp) ? (int)b2 : -1;
       }
     }
-    if (it + 1 < EMIT_CELLS && cx + TILE_W < fw) prefetch(cx + TILE_W);
+    if (it + 1 < EMIT_CELLS && cy + TILE_H < fh) prefetch(cy + TILE_H);
     unsigned long long remaining = ~0ull;
 #if K1_PRIOR_IN_EMIT
-    const double cell_prior =
-        have_prior ? __dmul_rn(__ldg(pt.gy8 + cy), __ldg(pt.gx8 + cx)) : 0.0;
+    const int ly = it * TILE_H + ty;     // cell row inside the block
+    const double cell_prior = have_prior ? __dmul_rn(s_gy8[ly], s_T[tx][32]) : 0.0;
     double emitted_prior = 0.0;
     bool can_complement = true;
 #endif
@@ -1107,7 +1134,13 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
             // last label of the cell: whole-cell prior minus what the other labels took
             pr = __dadd_rn(cell_prior, -emitted_prior);
           } else {
-            pr = pair_prior(pt, cy, cx, packed, lo, hi);
+            pr = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
+              const double rs = __dadd_rn(s_T[tx][b & 15u], s_T[tx][16 + (b >> 4)]);
+              pr = __fma_rn(s_gy[ly * 8 + r], rs, pr);
+            }
             emitted_prior = __dadd_rn(emitted_prior, pr);
           }
         }
@@ -1478,18 +1511,20 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
     S8Ws w8;
     carve_s8(w8, aligned, fh, fw, n_rows, nnz_cap);
     init_s8_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, fh, fw, gy, gx, nnz_flags);
-    dim3 egrid((fw + TILE_W * EMIT_CELLS - 1) / (TILE_W * EMIT_CELLS), (fh + TILE_H - 1) / TILE_H,
-               n_img);
+    dim3 egrid((fw + TILE_W - 1) / TILE_W,
+               (fh + TILE_H * EMIT_CELLS - 1) / (TILE_H * EMIT_CELLS), n_img);
     constexpr int NT = TILE_W * TILE_H;
     const PriorTabs pt{w8.gyT, fh, w8.gxT, w8.gx8, w8.gy8};
     if (label_dtype == SPALIGN_I32) {
-      const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4);
+      const size_t tab = (size_t)(TILE_W * 33 + EMIT_CELLS * TILE_H * 9) * sizeof(double);
+      const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4) + tab;
       SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int32_t>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       emit_s8v2_kernel<int32_t><<<egrid, NT, smem, stream>>>(
           (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
     } else {
-      const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4);
+      const size_t tab = (size_t)(TILE_W * 33 + EMIT_CELLS * TILE_H * 9) * sizeof(double);
+      const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4) + tab;
       SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int64_t>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       emit_s8v2_kernel<int64_t><<<egrid, NT, smem, stream>>>(

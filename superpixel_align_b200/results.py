@@ -70,3 +70,68 @@ def save_info(out_dir, img_fn, label_fn, road_mask, clustering_result, scores, a
     with open(os.path.join(out_dir, 'result.json'), 'a') as fp:
         print(json.dumps(info), file=fp)
     return info
+
+
+# ---------------------------------------------------------------------------------------------
+# Archives the downstream SegNet trainer reads
+# ---------------------------------------------------------------------------------------------
+def zip_estimated_labels(result_dir, zip_fn, pattern='*leftImg8bit.npy', root=None):
+    """``find <result_dir> -name "*leftImg8bit.npy" | zip -0r <zip_fn> -@`` (README.md:134-136):
+    an UNCOMPRESSED zip whose members keep the path ``find`` prints (relative to ``root``, default
+    the current directory).  datasets/zipped_estimated_cityscapes_dataset.py:20-24,65-66 opens it
+    with ``np.load`` and indexes members by that path.  Returns the member names."""
+    import fnmatch
+    import zipfile
+    root = os.getcwd() if root is None else root
+    names = []
+    for d, _, files in sorted(os.walk(result_dir)):
+        for fn in sorted(files):
+            if fnmatch.fnmatch(fn, pattern):
+                names.append(os.path.join(d, fn))
+    with zipfile.ZipFile(zip_fn, 'w', compression=zipfile.ZIP_STORED, allowZip64=True) as zf:
+        out = []
+        for path in names:
+            arc = os.path.relpath(path, root)
+            zf.write(path, arcname=arc)
+            out.append(arc)
+    return out
+
+
+class LabelZipWriter:
+    """The same archive written directly from masks (no intermediate .npy files): one stored
+    ``<prefix>/<stem>.npy`` member per image, uint8 like save_info (:393-394)."""
+
+    def __init__(self, zip_fn, prefix='results/estimated_train_labels'):
+        import zipfile
+        self.zf = zipfile.ZipFile(zip_fn, 'w', compression=zipfile.ZIP_STORED, allowZip64=True)
+        self.prefix = prefix
+        self.names = []
+
+    def add(self, img_fn, road_mask, suffix=''):
+        import io
+        stem = os.path.splitext(os.path.basename(img_fn))[0] + suffix
+        rm = road_mask.cpu().numpy() if isinstance(road_mask, torch.Tensor) else np.asarray(road_mask)
+        buf = io.BytesIO()
+        np.save(buf, rm.astype(np.uint8))
+        arc = '%s/%s.npy' % (self.prefix, stem)
+        self.zf.writestr(arc, buf.getvalue())
+        self.names.append(arc)
+        return arc
+
+    def close(self):
+        self.zf.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def save_label_npz(zip_fn, preds_and_scores):
+    """``np.savez(fp, **d)`` of utils/run_train_rounds.py:191-203: one archive holding, per
+    image, the predicted label and its score map under the keys the relabel workers queue."""
+    with open(zip_fn, 'wb') as fp:
+        np.savez(fp, **{k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                        for k, v in preds_and_scores.items()})
+    return zip_fn

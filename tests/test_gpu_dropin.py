@@ -276,9 +276,9 @@ def test_gapped_label_ids_follow_the_reference(golden_dir):
     bsk.clear_cache()
     w = bsk.batch_create_prior(args, labs)
     np.testing.assert_allclose(w, g['weights'], rtol=1e-12)
-    feats = np.zeros((2, 6, 4, 8), dtype=np.float32)
+    feats = np.zeros((2, 8, 4, 8), dtype=np.float32)
     f, got_n = bsk.batch_superpixel_align(args, None, None, labs, feats)
-    assert got_n == n_per and f.shape == (sum(n_per), 8)
+    assert got_n == n_per and f.shape == (sum(n_per), 10)
     cres, road = bsk.weighted_kmeans(labs, g['feats'], g['weights'], int(g['k']), n_per,
                                      init_assign=g['init'])
     assert np.array_equal(cres, g['cluster_map']) and np.array_equal(road, g['road'])

@@ -109,3 +109,45 @@ def test_global_kmeans_protocol_gloo_world2():
     for p in procs:
         p.join(30)
     assert res == {0: 'ok', 1: 'ok'}, res
+
+
+def test_label_archives_read_back_like_the_reference_dataset(tmp_path):
+    """zip -0 of *leftImg8bit.npy (README.md:134-136) and np.savez label zips
+    (utils/run_train_rounds.py:191-203), read the way
+    datasets/zipped_estimated_cityscapes_dataset.py:20-24,65-66 reads them."""
+    import zipfile
+    from superpixel_align_b200 import results
+    rs = np.random.RandomState(0)
+    out_dir = tmp_path / 'results' / 'estimated_train_labels'
+    out_dir.mkdir(parents=True)
+    masks = {}
+    for city, seq in (('aachen', '000000_000019'), ('bochum', '000000_000313')):
+        stem = '%s_%s_leftImg8bit' % (city, seq)
+        m = (rs.rand(16, 32) < 0.4).astype(np.uint8)
+        masks[stem] = m
+        np.save(out_dir / (stem + '.npy'), m)
+        np.save(out_dir / (stem + '_all_cluster.npy'), m * 3)      # must NOT be archived
+    zfn = str(tmp_path / 'estimated_train_labels.0.zip')
+    names = results.zip_estimated_labels(str(out_dir), zfn, root=str(tmp_path))
+    assert sorted(names) == sorted('results/estimated_train_labels/%s.npy' % s for s in masks)
+    with zipfile.ZipFile(zfn) as zf:
+        assert all(i.compress_type == zipfile.ZIP_STORED for i in zf.infolist())
+        label_fns = {'_'.join(os.path.basename(fn).split('_')[:3]): fn
+                     for fn in zf.namelist() if fn.endswith('leftImg8bit.npy')}
+    loaded = np.load(zfn)
+    for stem, m in masks.items():
+        key = '_'.join(stem.split('_')[:3])
+        assert np.array_equal(loaded[label_fns[key]].astype(np.int32), m)
+    # the direct writer produces the same archive content
+    zfn2 = str(tmp_path / 'direct.zip')
+    with results.LabelZipWriter(zfn2) as w:
+        for stem, m in masks.items():
+            w.add('/data/leftImg8bit/train/x/%s.png' % stem, m)
+    loaded2 = np.load(zfn2)
+    for stem, m in masks.items():
+        assert np.array_equal(loaded2['results/estimated_train_labels/%s.npy' % stem], m)
+    # np.savez label archives
+    d = {'a_leftImg8bit': masks[next(iter(masks))], 'a_leftImg8bit_scores': rs.rand(2, 4, 4).astype(np.float32)}
+    zfn3 = results.save_label_npz(str(tmp_path / 'iter-10_eval-train.0.zip'), d)
+    back = np.load(zfn3)
+    assert set(back.files) == set(d) and all(np.array_equal(back[k], v) for k, v in d.items())

@@ -13,7 +13,7 @@ from superpixel_align_b200 import ops, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device('cuda', 0)
-pool = min(n, 16)
+pool = n   # distinct maps: a small pool would sit in the 126 MB L2 and flatter K1 (round 2 lesson)
 base = synth.voronoi_labels_torch(pool, 1024, 2048, 25, 40, device=dev)
 labels = base.repeat((n + pool - 1) // pool, 1, 1)[:n].contiguous()
 n_sp = [1000] * n
