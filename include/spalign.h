@@ -284,6 +284,25 @@ int spalign_kmeans_init(const double* w, const int64_t* group_off, int G,
                         const int32_t* shuffled, const int64_t* shuf_off, int32_t* assign,
                         int32_t* m_out, spalign_stream_t stream);
 
+/* ---- f3: SLIC superpixels ---------------------------------------------------------------
+ * Replaces batch_superpixel() batch_spalign_kmeans.py:299-313 for --superpixel_method slic
+ * (skimage.segmentation.slic(img.transpose(1, 2, 0), n_segments), one image at a time on the CPU).
+ * scikit-image 0.13.1 is not in the reference tree: the contract is the published algorithm of
+ * that version as restated in oracle/spalign_oracle.py:slic (regular seed grid, k-means in
+ * (y, x, L, a, b) over 2*step windows, lower id wins ties, max_iter, 4-connectivity enforcement
+ * with min_size = min_size_factor * H*W / n_segments); colours quantised to 2^-12 and integer
+ * centre sums make the result bit-reproducible.  PARITY UNPINNED by the reference.
+ *   images  [n_img, 3, H, W] float32 (CHW, the layout the reference holds; values in 0..1)
+ *   labels  [n_img, H, W] int32 out: contiguous ids 0..S-1 in raster order of first pixels
+ *   n_labels[n_img] int32 out: S per image
+ * spalign_slic_segments = number of seeds of the grid (the cluster count before connectivity). */
+int spalign_slic_segments(int H, int W, int n_segments);
+size_t spalign_slic_workspace_bytes(int n_img, int H, int W, int n_segments);
+int spalign_slic(const float* images, int n_img, int H, int W, int n_segments, double compactness,
+                 int max_iter, int convert2lab, int enforce_connectivity, double min_size_factor,
+                 int32_t* labels, int32_t* n_labels, void* workspace, size_t ws_bytes,
+                 spalign_stream_t stream);
+
 /* ---- K4: paint-back -------------------------------------------------------------------
  * Replaces the double loop of weighted_kmeans() batch_spalign_kmeans.py:193-199 and the
  * `== 0` road mask (:207): cluster_map[p] = table[sp_off[img] + label[p]] (0 when the label

@@ -460,3 +460,156 @@ def pool_weighted(indptr, indices, wvals, feat_cellmajor, area):
         a, b = indptr[s], indptr[s + 1]
         out[s] = np.asarray(wvals[a:b]) @ F[indices[a:b]]
     return out / np.asarray(area, dtype=np.float64)[:, None]
+
+
+# --------------------------------------------------------------------------------------
+# f3. SLIC superpixels (batch_superpixel, batch_spalign_kmeans.py:299-313:
+#     skimage.segmentation.slic(img.transpose(1, 2, 0), n_segments)).
+# --------------------------------------------------------------------------------------
+# scikit-image 0.13.1 is not installed and not in the tree: PARITY UNPINNED.  This restates the
+# published algorithm of that version (segmentation/slic_superpixels.py + _slic.pyx: regular
+# seed grid, k-means in (y, x, L, a, b) restricted to 2*step windows, ties to the lower segment
+# id, max_iter = 10, then 4-connectivity enforcement with min_size = 0.5 * H * W / n_segments) with
+# two choices that make a GPU implementation bit-reproducible against it:
+#   * colours are quantised to multiples of 2^-12 after the Lab conversion and the division by
+#     the compactness, centre sums are integers (exact, order independent);
+#   * a component smaller than min_size joins the segment of the pixel LEFT of its first
+#     (raster-order) pixel, else the one ABOVE it (skimage takes the last labelled neighbour its
+#     flood fill met; both are "an adjacent segment visited earlier").  Final ids are numbered in
+#     raster order of each segment's first pixel, as skimage numbers them.
+SLIC_Q = 4096.0
+
+
+def rgb2lab(rgb):
+    """skimage.color.rgb2lab (D65, 2 degree observer) on float input as given (no rescale: the
+    reference hands 0..255 floats to slic, so the conversion runs on 0..255 -- kept)."""
+    arr = np.asarray(rgb, dtype=np.float64)
+    mask = arr > 0.04045
+    lin = np.where(mask, np.power((arr + 0.055) / 1.055, 2.4), arr / 12.92)
+    m = np.array([[0.412453, 0.357580, 0.180423],
+                  [0.212671, 0.715160, 0.072169],
+                  [0.019334, 0.119193, 0.950227]])
+    xyz = lin @ m.T
+    xyz = xyz / np.array([0.95047, 1.0, 1.08883])
+    mask = xyz > 0.008856
+    f = np.where(mask, np.cbrt(xyz), 7.787 * xyz + 16.0 / 116.0)
+    L = 116.0 * f[..., 1] - 16.0
+    a = 500.0 * (f[..., 0] - f[..., 1])
+    b = 200.0 * (f[..., 1] - f[..., 2])
+    return np.stack([L, a, b], axis=-1)
+
+
+def slic_grid(H, W, n_segments):
+    """skimage.util.regular_grid for a (1, H, W) volume: (start_y, step_y, start_x, step_x)."""
+    step = (H * W / float(n_segments)) ** 0.5
+    if H < step:                          # a dimension shorter than the step keeps all of it
+        sy, sx = float(H), (H * W / float(n_segments)) / H
+    elif W < step:
+        sy, sx = (H * W / float(n_segments)) / W, float(W)
+    else:
+        sy = sx = step
+    y0, x0 = int(sy // 2), int(sx // 2)
+    return y0, max(1, int(round(sy))), x0, max(1, int(round(sx)))
+
+
+def slic_quantise(img_chw, compactness=10.0, convert2lab=True):
+    """[3, H, W] float image -> int32 [H, W, 3] colours in units of 2^-12 (Lab / compactness)."""
+    hwc = np.asarray(img_chw, dtype=np.float32).transpose(1, 2, 0).astype(np.float64)
+    col = rgb2lab(hwc) if convert2lab else hwc
+    return np.rint(col * (1.0 / compactness) * SLIC_Q).astype(np.int64)
+
+
+def slic(img_chw, n_segments=100, compactness=10.0, max_iter=10, convert2lab=True,
+         enforce_connectivity=True, min_size_factor=0.5, return_raw=False):
+    """Label map int32 [H, W] with contiguous ids 0..S-1 (every id present)."""
+    q = slic_quantise(img_chw, compactness, convert2lab)
+    H, W, _ = q.shape
+    y0, sy, x0, sx = slic_grid(H, W, n_segments)
+    gy, gx = np.arange(y0, H, sy), np.arange(x0, W, sx)
+    ny, nx = len(gy), len(gx)
+    step = float(max(sy, sx))
+    cy = np.repeat(gy, nx).astype(np.float64)
+    cx = np.tile(gx, ny).astype(np.float64)
+    cc = q[np.repeat(gy, nx), np.tile(gx, ny)].astype(np.float64) / SLIC_Q
+    n_seg = ny * nx
+    wsp = 1.0 / (step * step)
+    col = q.astype(np.float64) / SLIC_Q
+    nearest = np.zeros((H, W), dtype=np.int64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for _ in range(max_iter):
+        dist = np.full((H, W), np.inf)
+        new = nearest.copy()
+        for k in range(n_seg):           # ascending k, strict '<': the lower id wins ties
+            if not np.isfinite(cy[k]):
+                continue
+            ya = int(max(cy[k] - 2 * sy, 0)); yb = int(min(cy[k] + 2 * sy + 1, H))
+            xa = int(max(cx[k] - 2 * sx, 0)); xb = int(min(cx[k] + 2 * sx + 1, W))
+            dy = cy[k] - yy[ya:yb, xa:xb]
+            dx = cx[k] - xx[ya:yb, xa:xb]
+            d = (dy * dy + dx * dx) * wsp
+            dc = col[ya:yb, xa:xb] - cc[k]
+            d = d + ((dc[..., 0] * dc[..., 0] + dc[..., 1] * dc[..., 1]) + dc[..., 2] * dc[..., 2])
+            upd = d < dist[ya:yb, xa:xb]
+            dist[ya:yb, xa:xb][upd] = d[upd]
+            new[ya:yb, xa:xb][upd] = k
+        changed = not np.array_equal(new, nearest)
+        nearest = new
+        if not changed:
+            break
+        cnt = np.bincount(nearest.ravel(), minlength=n_seg).astype(np.float64)
+        sum_y = np.bincount(nearest.ravel(), weights=yy.ravel(), minlength=n_seg)
+        sum_x = np.bincount(nearest.ravel(), weights=xx.ravel(), minlength=n_seg)
+        has = cnt > 0
+        cy = np.where(has, sum_y / np.where(has, cnt, 1), cy)   # an empty segment keeps its centre
+        cx = np.where(has, sum_x / np.where(has, cnt, 1), cx)
+        for c in range(3):
+            sc = np.zeros(n_seg, dtype=np.int64)
+            np.add.at(sc, nearest.ravel(), q[..., c].ravel())
+            cc[:, c] = np.where(has, (sc.astype(np.float64) / SLIC_Q) / np.where(has, cnt, 1), cc[:, c])
+    if return_raw or not enforce_connectivity:
+        if return_raw:
+            return nearest.astype(np.int32)
+        _, inv = np.unique(nearest, return_inverse=True)
+        return inv.reshape(H, W).astype(np.int32)
+    return slic_enforce_connectivity(nearest, int(min_size_factor * H * W / float(n_segments)))
+
+
+def slic_enforce_connectivity(nearest, min_size):
+    """4-connected components of the cluster map; components below min_size join the segment left
+    of (else above) their first pixel; ids renumbered in raster order of first pixels."""
+    from scipy import ndimage
+    H, W = nearest.shape
+    comp = np.zeros((H, W), dtype=np.int64)
+    n_comp = 0
+    for v in np.unique(nearest):
+        lab, n = ndimage.label(nearest == v)
+        comp[lab > 0] = lab[lab > 0] + n_comp
+        n_comp += n
+    # root = first (minimum) linear index of each component
+    lin = np.arange(H * W).reshape(H, W)
+    root = ndimage.minimum(lin, comp, index=np.arange(1, n_comp + 1)).astype(np.int64)
+    size = np.bincount(comp.ravel(), minlength=n_comp + 1)[1:]
+    root_map = root[comp - 1]                      # per pixel: root index of its component
+    target = {}
+    order = np.argsort(root)
+    for ci in order:                               # ascending first pixel: targets are final
+        r = int(root[ci])
+        if size[ci] >= min_size:
+            continue
+        y, x = divmod(r, W)
+        if x > 0:
+            t = int(root_map[y, x - 1])
+        elif y > 0:
+            t = int(root_map[y - 1, x])
+        else:
+            continue
+        target[r] = target.get(t, t)
+    if target:
+        keys = np.array(sorted(target))
+        vals = np.array([target[k] for k in keys])
+        idx = np.searchsorted(keys, root_map)
+        idx_c = np.clip(idx, 0, len(keys) - 1)
+        hit = keys[idx_c] == root_map
+        root_map = np.where(hit, vals[idx_c], root_map)
+    _, inv = np.unique(root_map, return_inverse=True)
+    return inv.reshape(H, W).astype(np.int32)

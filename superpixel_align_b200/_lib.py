@@ -55,6 +55,9 @@ SIGNATURES = {
     'spalign_kmeans_update': (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     'spalign_kmeans_debug_stats': (_i, [C.POINTER(C.c_int64), _i]),
     'spalign_kmeans_init': (_i, [_p, _p, _i, _p, _p, _p, _p, _p]),
+    'spalign_slic_segments': (_i, [_i, _i, _i]),
+    'spalign_slic_workspace_bytes': (_z, [_i, _i, _i, _i]),
+    'spalign_slic': (_i, [_p, _i, _i, _i, _i, _d, _i, _i, _i, _d, _p, _p, _p, _z, _p]),
     'spalign_paint': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p]),
     'spalign_refine': (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p]),
     'spalign_confusion2': (_i, [_p, _p, _i, _l, _p, _p]),

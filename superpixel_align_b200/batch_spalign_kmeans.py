@@ -37,7 +37,7 @@ import torch
 
 from . import _lib, ops
 
-__all__ = ['BatchState', 'prepare_batch', 'create_prior', 'weighted_average', 'kmeans', 'weighted_kmeans', 'superpixel_align',
+__all__ = ['BatchState', 'prepare_batch', 'batch_superpixel', 'create_prior', 'weighted_average', 'kmeans', 'weighted_kmeans', 'superpixel_align',
            'batch_superpixel_align', 'batch_create_prior', 'batch_weighted_kmeans',
            'estimate_road_mask']
 
@@ -335,6 +335,29 @@ def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, a
     if as_numpy:
         return _features_to_host(st, feat, append_pos)  # reference dtypes (:270)
     return feat
+
+
+def batch_superpixel(args, imgs):
+    """Label maps of a batch -- batch_spalign_kmeans.py:299-313 for ``--superpixel_method slic``
+    (``slic(img.transpose(1, 2, 0), args.n_slic_segments)``), on the device.
+
+    imgs [n, 3, H, W] float (0..255 as the reference holds them); returns int64 NumPy [n, H, W] for
+    NumPy input (what skimage yields), int32 CUDA for torch input.  The images are divided by 255
+    first: skimage 0.13 refuses float images outside [-1, 1] (``img_as_float``), so the
+    reference's slic branch -- which none of its shipped drivers uses -- only runs on scaled
+    input; its felzenszwalb branch (:303-307) scales by ``/ 255.`` itself.  Parity with skimage
+    is unpinned (not in the tree): the contract is oracle/spalign_oracle.py:slic.
+    felzenszwalb is not built (label maps are an input of the hot path)."""
+    method = getattr(args, 'superpixel_method', 'slic')
+    if method != 'slic':
+        raise NotImplementedError("superpixel_method %r: only 'slic' runs on the device; pass label "
+                                  "maps computed elsewhere to the batch_* functions" % method)
+    iu = _unwrap(imgs)
+    as_numpy = not isinstance(iu, torch.Tensor)
+    dev = _device(args) if as_numpy else iu.device
+    x = _to_dev(iu, dev, torch.float32) / 255.0
+    labels, _ = ops.slic(x, int(getattr(args, 'n_slic_segments', 100)))
+    return labels.cpu().numpy().astype(np.int64) if as_numpy else labels
 
 
 def batch_superpixel_align(args, model, imgs, superpixels, feature_maps):

@@ -72,9 +72,46 @@ class DRNC26(nn.Module):
         return (x, maps) if out_middle else x
 
 
-def drn_c_26(seed=1111, device='cuda', channels_last=True):
+def fold_batchnorm(model):
+    """Inference-time folding of every Conv2d -> BatchNorm2d pair into one convolution with bias
+    (same function in exact arithmetic; removes one full pass over each activation map)."""
+    def fold_seq(seq):
+        mods = list(seq.children())
+        out, i = [], 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                bn = mods[i + 1]
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                conv = nn.Conv2d(m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding,
+                                 dilation=m.dilation, bias=True)
+                conv.weight.data = m.weight.data * scale.view(-1, 1, 1, 1)
+                b0 = m.bias.data if m.bias is not None else torch.zeros_like(bn.running_mean)
+                conv.bias.data = (b0 - bn.running_mean) * scale + bn.bias
+                out.append(conv)
+                i += 2
+            else:
+                out.append(m)
+                i += 1
+        return nn.Sequential(*out)
+
+    def walk(mod):
+        for name, child in list(mod.named_children()):
+            if isinstance(child, nn.Sequential) and any(isinstance(c, nn.BatchNorm2d) for c in child.children()):
+                setattr(mod, name, fold_seq(child))
+            else:
+                walk(child)
+    with torch.no_grad():
+        walk(model)
+    return model
+
+
+def drn_c_26(seed=1111, device='cuda', channels_last=True, fold_bn=False):
     torch.manual_seed(seed)
-    m = DRNC26().eval().to(device)
+    m = DRNC26().eval()
+    if fold_bn:
+        m = fold_batchnorm(m)
+    m = m.to(device)
     if channels_last:
         m = m.to(memory_format=torch.channels_last)
     for p in m.parameters():

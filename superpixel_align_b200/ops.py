@@ -23,7 +23,7 @@ LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 # kernel launches per entry point (kept in sync with csrc/*.cu)
 _LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
                     kmeans_sweep=1, kmeans_finish=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
-                    refine=2, confusion2=1)
+                    refine=2, confusion2=1, slic=0)
 
 
 def _count(name):
@@ -652,6 +652,33 @@ def kmeans_init_device(w: torch.Tensor, group_off: torch.Tensor, shuffled: torch
 
 
 # --------------------------------------------------------------------------------------
+def slic(images: torch.Tensor, n_segments: int = 100, compactness: float = 10.0, max_iter: int = 10,
+         convert2lab: bool = True, enforce_connectivity: bool = True, min_size_factor: float = 0.5,
+         chunk: int = 16):
+    """f3: SLIC label maps on the device.  images [n, 3, H, W] float32 CUDA (values in 0..1) ->
+    (labels int32 [n, H, W] with contiguous ids, n_labels int32 [n]).  Contract and oracle:
+    oracle/spalign_oracle.py:slic (parity unpinned: scikit-image is not in the reference tree)."""
+    global LAUNCHES
+    _require_cuda(images)
+    assert images.dim() == 4 and images.shape[1] == 3
+    images = images.float().contiguous()
+    n, _, H, W = images.shape
+    dev = images.device
+    lib = _lib.load()
+    labels = torch.empty((n, H, W), dtype=torch.int32, device=dev)
+    n_labels = torch.empty(n, dtype=torch.int32, device=dev)
+    ws_bytes = lib.spalign_slic_workspace_bytes(min(chunk, n), H, W, int(n_segments))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        check(lib.spalign_slic(_ptr(images[i:i + m]), m, H, W, int(n_segments), float(compactness),
+                               int(max_iter), int(convert2lab), int(enforce_connectivity),
+                               float(min_size_factor), _ptr(labels[i:i + m]), _ptr(n_labels[i:i + m]),
+                               _ptr(ws), ws_bytes, _stream()), 'slic')
+        LAUNCHES += 3 + 5 * int(max_iter) + (30 if enforce_connectivity else 3) + 3
+    return labels, n_labels
+
+
 _OUT_CODES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
 
 

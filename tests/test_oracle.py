@@ -237,3 +237,26 @@ def test_inline_reference_code_live():
     with pytest.raises(ValueError):
         ref_extract.load_inline('superpixel_overlaps.py', 'estimate_road_mask', 361, 369, 'f',
                                 ['road_mask', 'superpixel', 'args'], ['refined_roadmap'])
+
+
+def test_slic_oracle_contract():
+    """The SLIC restatement (parity unpinned: scikit-image absent): contiguous ids numbered in
+    raster order, 4-connected segments, seed grid of skimage.util.regular_grid."""
+    from scipy import ndimage
+    rs = np.random.RandomState(0)
+    img = ndimage.uniform_filter(rs.rand(3, 64, 96), (0, 9, 9)).astype(np.float32)
+    img = (img - img.min()) / (img.max() - img.min())
+    assert so.slic_grid(1024, 2048, 1000) == (22, 46, 22, 46)
+    assert so.slic_grid(224, 224, 100) == (11, 22, 11, 22)
+    raw = so.slic(img, 24, return_raw=True)
+    assert len(np.unique(raw)) == 24
+    lab = so.slic(img, 24)
+    S = lab.max() + 1
+    assert len(np.unique(lab)) == S and lab[0, 0] == 0
+    first = np.full(S, lab.size)
+    np.minimum.at(first, lab.ravel(), np.arange(lab.size))
+    assert np.all(np.diff(first) > 0)
+    assert all(ndimage.label(lab == v)[1] == 1 for v in range(S))
+    # known answer of the Lab conversion (skimage.color.rgb2lab of pure white / mid grey)
+    np.testing.assert_allclose(so.rgb2lab(np.array([1.0, 1.0, 1.0])), [100.0, -0.00245, 0.00465], atol=2e-5)
+    np.testing.assert_allclose(so.rgb2lab(np.array([0.5, 0.5, 0.5]))[0], 53.389, atol=2e-3)
