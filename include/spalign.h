@@ -139,6 +139,27 @@ int spalign_overlap_bilinear_csr(const void* labels, int label_dtype, int n_img,
                                  double* row_weight, int64_t* nnz_flags, void* workspace,
                                  size_t ws_bytes, spalign_stream_t stream);
 
+/* ---- f2: anchor-sampled superpixel align (the reference's own pooling) -------------------
+ * superpixel_align() batch_spalign_kmeans.py:226-274: n_select member pixels per superpixel
+ * ("anchors"), each sampled bilinearly from the 4 nearest cell centres, averaged.
+ * spalign_sample_anchors draws the anchors on the device (uniform over the members, distinct,
+ * counter-based hash of (seed, row, draw); the reference's random.shuffle stream (:232) cannot
+ * be replayed -- pass anchors computed elsewhere to reproduce it):
+ *   anchors [n_rows, n_select, 2] int32 (y, x) pixels, -1 padded; n_valid [n_rows] int32
+ * spalign_anchor_weights turns anchors into a CSR of 4 * n_select (cell, weight) entries per row
+ * -- feature coordinates pixel * (fh / H) + 0.5 clipped to [0, f - 0.5] (:215, :235-240), 4
+ * nearest centres with ties to the lower cell index (the reference's argsort is unstable there),
+ * bounding-box corners and bilinear weights (:247-266), divided by n_valid -- for
+ * spalign_pool_weighted (pass an all-ones `area`). */
+int spalign_sample_anchors(const void* labels, int label_dtype, int n_img, int H, int W, int fh,
+                           int fw, const int64_t* sp_off, int64_t n_rows, const int32_t* indptr,
+                           const int32_t* indices, const int32_t* counts, const int32_t* area,
+                           int n_select, uint64_t seed, int32_t* anchors, int32_t* n_valid,
+                           spalign_stream_t stream);
+int spalign_anchor_weights(const int32_t* anchors, const int32_t* n_valid, int64_t n_rows,
+                           int n_select, int H, int fh, int fw, int32_t* indptr, int32_t* indices,
+                           double* wvals, spalign_stream_t stream);
+
 /* Layout helper: [n_img, C, ncell] (NCHW, what F.concat yields at batch_spalign_kmeans.py:435)
  * -> [n_img, ncell, C] cell-major.  direct_clustering.py:302 does the same transpose. */
 int spalign_nchw_to_cellmajor(const float* src, float* dst, int n_img, int C, int ncell,

@@ -226,6 +226,40 @@ def gen_gapped():
     print('gapped_ref.npz:', n_per, cres.shape)
 
 
+def gen_anchors():
+    """The reference's anchor-sampled superpixel_align (:210-276), run unmodified with
+    n_select = 1 and 10; the anchors it drew are recovered by replaying Python's ``random`` from
+    the same state.  ``tie_free`` marks anchors whose 4th and 5th nearest cell centres are not
+    equidistant: there the reference's unstable argsort cannot matter and the result is pinned."""
+    ref = ref_extract.load('batch_spalign_kmeans.py', seed=1111)
+    from oracle import spalign_oracle as so
+    H, W, fh, fw, C = 64, 128, 8, 16, 8
+    lab = synth.voronoi_labels(H, W, 5, 8, image_index=12, dtype=np.int64)
+    fm = synth.smooth_features(C, fh, fw, seed=9, radius=1)
+    img = np.zeros((3, H, W), dtype=np.float32)
+    yy, xx = np.meshgrid(np.arange(fh), np.arange(fw))
+    flat = (np.stack([yy, xx]).transpose(1, 2, 0) + 0.5).reshape(-1, 2)
+    out = dict(label=lab, feature_map=fm)
+    for n_select in (1, 10):
+        state = random.getstate()
+        f = ref.superpixel_align(img, fm, lab, n_select, 4, True)
+        random.setstate(state)
+        anchors, n_valid = so.replay_reference_anchors(lab, n_select)
+        tie_free = np.zeros(anchors.shape[:2], dtype=bool)
+        for s_ in range(anchors.shape[0]):
+            for a in range(int(n_valid[s_])):
+                py, px = so.anchor_to_feature_coords(int(anchors[s_, a, 0]), int(anchors[s_, a, 1]), H, fh, fw)
+                d2 = np.sort(((flat - np.array([py, px])) ** 2).sum(axis=1))
+                tie_free[s_, a] = d2[3] < d2[4]
+        out.update({'anchors_%d' % n_select: anchors.astype(np.int32),
+                    'n_valid_%d' % n_select: n_valid.astype(np.int32),
+                    'features_%d' % n_select: np.asarray(f, dtype=np.float64),
+                    'tie_free_%d' % n_select: tie_free})
+    np.savez_compressed(os.path.join(OUT, 'anchors_ref.npz'), **out)
+    print('anchors_ref.npz:', out['features_10'].shape, 'tie-free anchors',
+          float(out['tie_free_10'].mean()))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     random.seed(1111)
@@ -236,3 +270,4 @@ if __name__ == '__main__':
     gen_refine()
     gen_direct()
     gen_gapped()
+    gen_anchors()

@@ -613,3 +613,77 @@ def slic_enforce_connectivity(nearest, min_size):
         root_map = np.where(hit, vals[idx_c], root_map)
     _, inv = np.unique(root_map, return_inverse=True)
     return inv.reshape(H, W).astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# f2. anchor-sampled superpixel align (the reference's own pooling, batch_spalign_kmeans.py:234-274)
+# --------------------------------------------------------------------------------------
+# Deterministic part restated: given the anchor pixels of a superpixel, each anchor is mapped to
+# feature coordinates p = pixel * (fh / H) + 0.5 (the HEIGHT ratio for both axes, :215), clipped
+# to [0, f - 0.5] (:237-240); the n_neighbor = 4 nearest cell centres (i + 0.5, j + 0.5) are
+# found (:244-246); their bounding box gives the four corner cells and the bilinear weights
+# (:247-266).  The reference's argsort is unstable: ties between equidistant centres (common,
+# because the coordinates are multiples of 1/8) are broken HERE by the lower flat cell index
+# (stable sort) -- the contract of the CUDA path.  Which pixels are anchors is random in the
+# reference (random.shuffle of the member list, :232); callers pass them in.
+
+
+def anchor_cells_weights(py, px, fh, fw):
+    """One anchor in feature coordinates -> ((c11, c12, c21, c22), (w11, w12, w21, w22)) with the
+    division by the box area folded into the weights (:257-266)."""
+    yy, xx = np.meshgrid(np.arange(fh), np.arange(fw))          # the reference's (transposed) grid
+    flat = (np.stack([yy, xx]).transpose(1, 2, 0) + 0.5).reshape(-1, 2)
+    cell = (flat[:, 0] - 0.5).astype(np.int64) * fw + (flat[:, 1] - 0.5).astype(np.int64)
+    d2 = ((flat - np.array([py, px])[None, :]) ** 2).sum(axis=1)
+    # stable order by (distance, flat cell index)
+    order = np.lexsort((cell, d2))[:4]
+    nb = flat[order]
+    max_y, max_x = nb.max(axis=0)
+    min_y, min_x = nb.min(axis=0)
+    area = (max_x - min_x) * (max_y - min_y)
+    cells = (int(min_y) * fw + int(min_x), int(max_y) * fw + int(min_x),
+             int(min_y) * fw + int(max_x), int(max_y) * fw + int(max_x))
+    w = ((max_x - px) * (max_y - py) / area, (max_x - px) * (py - min_y) / area,
+         (px - min_x) * (max_y - py) / area, (px - min_x) * (py - min_y) / area)
+    return cells, w
+
+
+def anchor_to_feature_coords(y, x, H, fh, fw):
+    r = float(fh) / H
+    py = min(max(y * r + 0.5, 0.0), fh - 1 + 0.5)
+    px = min(max(x * r + 0.5, 0.0), fw - 1 + 0.5)
+    return py, px
+
+
+def pool_anchors(feature_map, H, anchors, n_valid):
+    """feature_map [C, fh, fw]; anchors int [S, n, 2] (y, x) pixels, n_valid [S] -> [S, C]
+    float64: mean over the anchors of the bilinear sample (:242-274)."""
+    C, fh, fw = feature_map.shape
+    F = feature_map.reshape(C, -1).astype(np.float64)
+    out = np.zeros((anchors.shape[0], C))
+    for s in range(anchors.shape[0]):
+        acc = np.zeros(C)
+        for a in range(int(n_valid[s])):
+            py, px = anchor_to_feature_coords(int(anchors[s, a, 0]), int(anchors[s, a, 1]), H, fh, fw)
+            cells, w = anchor_cells_weights(py, px, fh, fw)
+            for c, wt in zip(cells, w):
+                acc += wt * F[:, c]
+        out[s] = acc / max(int(n_valid[s]), 1)
+    return out
+
+
+def replay_reference_anchors(label, n_select=10):
+    """The anchors the reference's superpixel_align draws for this label map from the CURRENT
+    state of Python's ``random`` (consumed exactly as :226-234 consumes it)."""
+    import random
+    ids = np.sort(np.unique(label))
+    anchors = np.full((len(ids), n_select, 2), -1, dtype=np.int64)
+    n_valid = np.zeros(len(ids), dtype=np.int64)
+    for i, idx in enumerate(ids):
+        y, x = np.where(label == idx)
+        coords = list(zip(y.tolist(), x.tolist()))
+        random.shuffle(coords)
+        sel = coords[:n_select]
+        anchors[i, :len(sel)] = np.asarray(sel)
+        n_valid[i] = len(sel)
+    return anchors, n_valid

@@ -35,6 +35,9 @@ SIGNATURES = {
     'spalign_overlap_bilinear_workspace_bytes': (_z, [_i, _i, _i, _i, _i, _l, _l]),
     'spalign_overlap_bilinear_csr': (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _l, _p, _p, _p, _p, _p, _p,
                                           _p, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p]),
+    'spalign_sample_anchors': (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _l, _p, _p, _p, _p, _i, C.c_uint64, _p,
+                                    _p, _p]),
+    'spalign_anchor_weights': (_i, [_p, _p, _l, _i, _i, _i, _i, _p, _p, _p, _p]),
     'spalign_nchw_to_cellmajor': (_i, [_p, _p, _i, _i, _i, _p]),
     'spalign_kmeans_groups_workspace_bytes': (_z, [_i, _i, _i]),
     'spalign_kmeans_groups': (_i, [_p, _i, _l, _i, _i, _l, _p, _i, _i, _i, _p, _i, _p, _p, _p,

@@ -285,10 +285,12 @@ def kmeans(k, X, weights=None, n_iter=1000, init_assign=None):
     return res.assign
 
 
-POOLING = 'count'   # module default; 'bilinear' = dense resize+mean of the notebook (f2)
+POOLING = 'count'   # module default; 'bilinear' = dense resize+mean of the notebook (f2);
+                    # 'anchor' = the reference's n_select random anchors per superpixel (f2)
+ANCHOR_SEED = 1111  # seed of the device anchor sampler (the reference seeds random with 1111, :33)
 
 
-def _features_for(st, feature_maps, dev, append_pos, pooling=None):
+def _features_for(st, feature_maps, dev, append_pos, pooling=None, n_select=None):
     fm = _unwrap(feature_maps)
     if isinstance(fm, (list, tuple)):
         fm = torch.stack([_to_dev(f, dev) for f in fm])
@@ -296,9 +298,15 @@ def _features_for(st, feature_maps, dev, append_pos, pooling=None):
     if fm.dim() == 3:
         fm = fm[None]
     cell = ops.as_cellmajor(fm)
-    if (pooling or POOLING) == 'bilinear':
+    mode = pooling or POOLING
+    if mode == 'bilinear':
         bw = ops.overlap_bilinear_csr(st.labels, st.fh, st.fw, st.ov)
         return ops.pool_weighted(cell, st.ov, bw, append_pos=append_pos)
+    if mode == 'anchor':
+        # the reference's own pooling (:226-274): n_select random member pixels per superpixel
+        anchors, n_valid = ops.sample_anchors(st.labels, st.ov, n_select or 10, ANCHOR_SEED)
+        return ops.pool_anchors(cell, st.ov, anchors, n_valid, st.labels.shape[-2],
+                                append_pos=append_pos)
     return ops.pool(cell, st.ov, append_pos=append_pos)
 
 
@@ -325,13 +333,14 @@ def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, a
                      pooling=None):
     """One descriptor per superpixel, [S, C(+2)] in sorted-label order
     (batch_spalign_kmeans.py:210-276; count pooling, see module docstring).
-    ``pooling='bilinear'`` = mean of the bilinearly resized map (Superpixel_Align.ipynb cell 4)."""
+    ``pooling='bilinear'`` = mean of the bilinearly resized map (Superpixel_Align.ipynb cell 4);
+    ``pooling='anchor'`` = the reference's own ``n_select`` random anchors with its bilinear rule."""
     fm = _unwrap(feature_map)
     as_numpy = not isinstance(fm, torch.Tensor)
     dev = _device() if as_numpy else fm.device
     fh, fw = fm.shape[-2:]
     st = _batch_state(superpixels, dev, fh, fw, None)
-    feat = _features_for(st, fm, dev, append_pos, pooling)
+    feat = _features_for(st, fm, dev, append_pos, pooling, n_select)
     if as_numpy:
         return _features_to_host(st, feat, append_pos)  # reference dtypes (:270)
     return feat
@@ -371,7 +380,8 @@ def batch_superpixel_align(args, model, imgs, superpixels, feature_maps):
     fh, fw = fm.shape[-2:]
     st = _batch_state(superpixels, dev, fh, fw, _prior_from_args(args))
     append_pos = not getattr(args, 'without_pos', False)
-    feat = _features_for(st, fm, dev, append_pos, getattr(args, 'spalign_pooling', None))
+    feat = _features_for(st, fm, dev, append_pos, getattr(args, 'spalign_pooling', None),
+                         getattr(args, 'n_anchors', None))
     n_per = [int(v) for v in st.n_sp]
     st.feat, st.feat_token = feat, None
     if as_numpy:

@@ -23,7 +23,7 @@ LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 # kernel launches per entry point (kept in sync with csrc/*.cu)
 _LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
                     kmeans_sweep=1, kmeans_finish=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
-                    refine=2, confusion2=1, slic=0)
+                    refine=2, confusion2=1, slic=0, sample_anchors=1, anchor_weights=1)
 
 
 def _count(name):
@@ -273,6 +273,60 @@ def pool_weighted(feat_cellmajor: torch.Tensor, ov: Overlap, bw: BilinearOverlap
         _ptr(bw.indptr), _ptr(bw.indices), _ptr(bw.wvals), _ptr(ov.area), _ptr(ov.sum_y),
         _ptr(ov.sum_x), int(append_pos), _ptr(out), ld, _stream()), 'pool_weighted')
     _count('pool_weighted')
+    return out[:, :D]
+
+
+def sample_anchors(labels: torch.Tensor, ov: Overlap, n_select: int = 10, seed: int = 1111):
+    """f2: n_select distinct member pixels per superpixel, uniform over the members (the
+    reference shuffles with Python's ``random``, batch_spalign_kmeans.py:232; this stream is a
+    statistical equivalent).  Returns (anchors int32 [n_rows, n_select, 2], n_valid int32)."""
+    _require_cuda(labels)
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    dev = labels.device
+    anchors = torch.empty((ov.n_rows, n_select, 2), dtype=torch.int32, device=dev)
+    n_valid = torch.empty(ov.n_rows, dtype=torch.int32, device=dev)
+    check(_lib.load().spalign_sample_anchors(
+        _ptr(labels), _label_code(labels), n, H, W, ov.fh, ov.fw, _ptr(ov.sp_off), ov.n_rows,
+        _ptr(ov.indptr), _ptr(ov.indices), _ptr(ov.counts), _ptr(ov.area), int(n_select),
+        int(seed) & 0xffffffffffffffff, _ptr(anchors), _ptr(n_valid), _stream()), 'sample_anchors')
+    _count('sample_anchors')
+    return anchors, n_valid
+
+
+def pool_anchors(feat_cellmajor: torch.Tensor, ov: Overlap, anchors: torch.Tensor,
+                 n_valid: torch.Tensor, H: int, append_pos: bool = True) -> torch.Tensor:
+    """f2: the reference's anchor-sampled descriptors (batch_spalign_kmeans.py:234-274) for
+    given anchors: [n_rows, C(+2)] float32 (centroid columns from the count matrix ``ov``)."""
+    _require_cuda(feat_cellmajor, anchors, n_valid)
+    n, ncell, C = feat_cellmajor.shape
+    assert n == ov.n_img and ncell == ov.fh * ov.fw and feat_cellmajor.is_contiguous()
+    dev = feat_cellmajor.device
+    anchors = anchors.to(torch.int32).contiguous()
+    n_valid = n_valid.to(torch.int32).contiguous()
+    R, n_select = anchors.shape[0], anchors.shape[1]
+    assert R == ov.n_rows
+    indptr = torch.empty(R + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(R * 4 * n_select, dtype=torch.int32, device=dev)
+    wvals = torch.empty(R * 4 * n_select, dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    check(lib.spalign_anchor_weights(_ptr(anchors), _ptr(n_valid), R, n_select, int(H), ov.fh, ov.fw,
+                                     _ptr(indptr), _ptr(indices), _ptr(wvals), _stream()),
+          'anchor_weights')
+    _count('anchor_weights')
+    D = C + (2 if append_pos else 0)
+    ld = padded_ld(D)
+    out = torch.empty((R, ld), dtype=torch.float32, device=dev)
+    ones = torch.ones(R, dtype=torch.int32, device=dev)     # the weights carry the 1 / n_valid
+    check(lib.spalign_pool_weighted(
+        _ptr(feat_cellmajor), n, C, ov.fh, ov.fw, _ptr(ov.sp_off), R, ov.max_rows, _ptr(indptr),
+        _ptr(indices), _ptr(wvals), _ptr(ones), _ptr(ov.sum_y), _ptr(ov.sum_x), 0, _ptr(out), ld,
+        _stream()), 'pool_weighted')
+    _count('pool_weighted')
+    if append_pos:
+        area = ov.area.to(torch.float64)
+        out[:, C] = (ov.sum_y.to(torch.float64) / area).float()
+        out[:, C + 1] = (ov.sum_x.to(torch.float64) / area).float()
     return out[:, :D]
 
 

@@ -653,3 +653,58 @@ def test_bilinear_overlap_and_pooling_match_oracle(ops, H, W, fh, fw, gy, gx, dt
         assert np.array_equal(got[S * i:S * (i + 1), C], (sy / area).astype(np.float32))
     bw2 = ops.overlap_bilinear_csr(t, fh, fw, ov)
     assert torch.equal(bw.wvals[:nnz], bw2.wvals[:nnz])            # bit-reproducible
+
+
+# ------------------------------------------------------------------- f2 anchor-sampled pooling
+def test_anchor_pooling_matches_oracle_and_reference_golden(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'anchors_ref.npz'))
+    lab, fm = g['label'], g['feature_map']
+    C, fh, fw = fm.shape
+    H, W = lab.shape
+    S = int(lab.max()) + 1
+    t = torch.from_numpy(lab[None]).to(dev())
+    ov = ops.overlap_csr(t, fh, fw, [S])
+    cell = ops.as_cellmajor(torch.from_numpy(fm[None]).to(dev()))
+    for n_select in (1, 10):
+        anchors, n_valid = g['anchors_%d' % n_select], g['n_valid_%d' % n_select]
+        got = ops.pool_anchors(cell, ov, torch.from_numpy(anchors).to(dev()),
+                               torch.from_numpy(n_valid).to(dev()), H, append_pos=True).cpu().numpy()
+        want_oracle = so.pool_anchors(fm, H, anchors, n_valid)         # same tie rule: all rows
+        np.testing.assert_allclose(got[:, :C], want_oracle, rtol=1e-5, atol=1e-6)
+        ref = g['features_%d' % n_select]                               # the reference itself
+        rows_ok = g['tie_free_%d' % n_select].all(axis=1)
+        np.testing.assert_allclose(got[rows_ok, :C], ref[rows_ok, :C], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(got[:, C:], ref[:, C:], rtol=1e-6)
+
+
+@pytest.mark.parametrize('H,W,fh,fw,gy,gx,dtype', [(64, 128, 8, 16, 4, 8, np.int32), (50, 70, 7, 9, 3, 4, np.int64)])
+def test_anchor_sampler_draws_distinct_member_pixels(ops, H, W, fh, fw, gy, gx, dtype):
+    labs = np.stack([synth.voronoi_labels(H, W, gy, gx, image_index=i, dtype=dtype) for i in range(2)])
+    labs[1][labs[1] == 1] = 0          # a big superpixel and a missing id (empty row) in image 1
+    S = gy * gx
+    t = torch.from_numpy(labs).to(dev())
+    ov = ops.overlap_csr(t, fh, fw, [S, S])
+    for n_select in (10, 3):
+        a, nv = ops.sample_anchors(t, ov, n_select, seed=5)
+        a2, _ = ops.sample_anchors(t, ov, n_select, seed=5)
+        a3, _ = ops.sample_anchors(t, ov, n_select, seed=6)
+        assert torch.equal(a, a2) and not torch.equal(a, a3)
+        a, nv = a.cpu().numpy(), nv.cpu().numpy()
+        area = ov.area.cpu().numpy()
+        assert np.array_equal(nv, np.minimum(area, n_select))
+        for r in range(2 * S):
+            img, s = divmod(r, S)
+            pts = a[r, :nv[r]]
+            assert (a[r, nv[r]:] == -1).all()
+            assert all(labs[img][y, x] == s for y, x in pts)
+            assert len({(int(y), int(x)) for y, x in pts}) == nv[r]
+    # roughly uniform over the members: every pixel of a small superpixel is drawn sometimes
+    small = int(np.argmin(np.where(ov.area.cpu().numpy()[:S] > 0, ov.area.cpu().numpy()[:S], 1 << 30)))
+    hits = {}
+    for seed in range(200):
+        a, nv = ops.sample_anchors(t, ov, 4, seed=seed)
+        for y, x in a[small, :int(nv[small])].cpu().numpy():
+            hits[(int(y), int(x))] = hits.get((int(y), int(x)), 0) + 1
+    n_px = int(ov.area[small].item())
+    expect = 200 * min(4, n_px) / n_px
+    assert len(hits) == n_px and max(hits.values()) < 2.5 * expect + 10

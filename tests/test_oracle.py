@@ -260,3 +260,25 @@ def test_slic_oracle_contract():
     # known answer of the Lab conversion (skimage.color.rgb2lab of pure white / mid grey)
     np.testing.assert_allclose(so.rgb2lab(np.array([1.0, 1.0, 1.0])), [100.0, -0.00245, 0.00465], atol=2e-5)
     np.testing.assert_allclose(so.rgb2lab(np.array([0.5, 0.5, 0.5]))[0], 53.389, atol=2e-3)
+
+
+def test_anchor_pooling_matches_reference_golden(golden_dir):
+    """anchors_ref.npz = the reference's superpixel_align (anchor path) with the anchors it drew:
+    wherever no tie between equidistant cell centres is involved the restatement is exact; the
+    centroid columns always are."""
+    g = np.load(os.path.join(golden_dir, 'anchors_ref.npz'))
+    lab, fm = g['label'], g['feature_map']
+    C = fm.shape[0]
+    H = lab.shape[0]
+    area, sy, sx = so.superpixel_stats(lab)
+    for n_select in (1, 10):
+        anchors, n_valid = g['anchors_%d' % n_select], g['n_valid_%d' % n_select]
+        want = g['features_%d' % n_select]
+        got = so.pool_anchors(fm, H, anchors, n_valid)
+        rows_ok = g['tie_free_%d' % n_select].all(axis=1) | (n_valid == 0)
+        assert rows_ok.sum() >= (20 if n_select == 1 else 1)
+        np.testing.assert_allclose(got[rows_ok], want[rows_ok, :C], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(want[:, C], sy / area, rtol=1e-14)      # center_of_mass: 1 ulp
+        np.testing.assert_allclose(want[:, C + 1], sx / area, rtol=1e-14)
+        # with ties the restatement may pick other (equidistant) corner cells: bounded effect
+        assert np.abs(got - want[:, :C]).max() < 0.5 * np.abs(want[:, :C]).max()
