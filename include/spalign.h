@@ -343,6 +343,13 @@ int spalign_refine(const int64_t* sp_off, int n_img, int64_t n_rows, int ncell,
                    const uint8_t* road_cell, double thr, int64_t* overlap, int64_t* road_px,
                    int32_t* keep, spalign_stream_t stream);
 
+/* Nearest-neighbour resize of uint8 maps [n_img, h, w] -> [n_img, H, W]: the
+ * cv.resize(road_mask / clustering_result, (w, h), interpolation=cv.INTER_NEAREST) that brings the
+ * estimates to the label shape before evaluation (batch_spalign_kmeans.py:470-477,
+ * direct_clustering.py:329-332, superpixel_overlaps.py:360-362). */
+int spalign_resize_nearest_u8(const uint8_t* src, int n_img, int h, int w, uint8_t* dst, int H,
+                              int W, spalign_stream_t stream);
+
 /* ---- evaluation -----------------------------------------------------------------------
  * Replaces chainercv calc_semantic_segmentation_confusion as used at
  * batch_spalign_kmeans.py:398-402 for 2 classes: conf[img, gt*2+pred] over pixels gt >= 0. */

@@ -63,6 +63,7 @@ SIGNATURES = {
     'spalign_slic': (_i, [_p, _i, _i, _i, _i, _d, _i, _i, _i, _d, _p, _p, _p, _z, _p]),
     'spalign_paint': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p]),
     'spalign_refine': (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p]),
+    'spalign_resize_nearest_u8': (_i, [_p, _i, _i, _i, _p, _i, _i, _p]),
     'spalign_confusion2': (_i, [_p, _p, _i, _l, _p, _p]),
 }
 

@@ -216,6 +216,32 @@ extern "C" int spalign_refine(const int64_t* sp_off, int n_img, int64_t n_rows, 
   return check_launch("refine");
 }
 
+// cv2.resize(..., interpolation=cv2.INTER_NEAREST): source index = min(floor(dst * ifx), src - 1)
+// with ifx = 1.0 / (dst_size / src_size) in double, as OpenCV computes it
+__global__ void __launch_bounds__(256)
+resize_nearest_u8_kernel(const uint8_t* __restrict__ src, int h, int w, uint8_t* __restrict__ dst,
+                         int H, int W, double sy, double sx) {
+  const int img = blockIdx.z;
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= W || y >= H) return;
+  const int yy = min((int)floor(__dmul_rn((double)y, sy)), h - 1);
+  const int xx = min((int)floor(__dmul_rn((double)x, sx)), w - 1);
+  dst[((size_t)img * H + y) * W + x] = src[((size_t)img * h + yy) * w + xx];
+}
+
+extern "C" int spalign_resize_nearest_u8(const uint8_t* src, int n_img, int h, int w, uint8_t* dst,
+                                         int H, int W, spalign_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SPALIGN_REQUIRE(src && dst && n_img > 0 && n_img <= 65535 && h > 0 && w > 0 && H > 0 && W > 0,
+                  "resize_nearest_u8: bad arguments");
+  const dim3 grid((W + 63) / 64, (H + 3) / 4, n_img);
+  // OpenCV: inv_scale = dst / src (double), ifx = 1.0 / inv_scale, sx = cvFloor(x * ifx)
+  const double ify = 1.0 / ((double)H / (double)h), ifx = 1.0 / ((double)W / (double)w);
+  resize_nearest_u8_kernel<<<grid, 256, 0, stream>>>(src, h, w, dst, H, W, ify, ifx);
+  return check_launch("resize_nearest_u8");
+}
+
 extern "C" int spalign_confusion2(const uint8_t* pred, const int32_t* gt, int n_img,
                                   int64_t n_pix, int64_t* conf, spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -36,10 +36,13 @@ nchw_to_cellmajor_kernel(const float* __restrict__ src, float* __restrict__ dst,
   }
 }
 
+#ifndef POOL_ALTERNATE
+#define POOL_ALTERNATE 1
+#endif
 // NACC float4 accumulators per thread: C = 4 * blockDim.x * NACC
 template <int NACC>
 __global__ void __launch_bounds__(256)
-pool_rows_kernel(const float* __restrict__ feat, int C, int ncell,
+pool_rows_kernel(const float* __restrict__ feat, int C, int ncell, int pool_fw,
                  const int64_t* __restrict__ sp_off, const int32_t* __restrict__ indptr,
                  const int32_t* __restrict__ indices, const int32_t* __restrict__ counts,
                  const double* __restrict__ wvals, const int32_t* __restrict__ area, const int64_t* __restrict__ sum_y,
@@ -63,12 +66,28 @@ pool_rows_kernel(const float* __restrict__ feat, int C, int ncell,
 #pragma unroll
   for (int a = 0; a < NACC; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // Cells on the border between two superpixels are read by both.  Superpixels in alternate
+  // bands of the image walk their cells in opposite directions (band = the row's middle cell
+  // row / the typical superpixel height), so vertical neighbours meet at their shared border
+  // at the same time -- both at the start or both at the end of their lives -- and the second
+  // read hits L2 instead of DRAM.  The order is a fixed function of the matrix: deterministic.
+  bool reverse = false;
+#if POOL_ALTERNATE
+  if (L > 0 && counts != nullptr) {
+    const int fw_ = pool_fw;
+    const float mid = 0.5f * (float)(indices[base] / fw_ + indices[base + L - 1] / fw_);
+    const float hc = sqrtf((float)ncell / (float)max(n_sp, 1));
+    reverse = ((int)(mid / fmaxf(hc, 1.f)) & 1) != 0;
+  }
+#endif
+
   for (int e0 = 0; e0 < L; e0 += 256) {
     const int n = min(256, L - e0);
     __syncthreads();
     for (int e = t; e < n; e += blockDim.x) {
-      s_idx[e] = indices[base + e0 + e];
-      s_cnt[e] = counts != nullptr ? (float)counts[base + e0 + e] : (float)wvals[base + e0 + e];
+      const int src = reverse ? base + L - 1 - (e0 + e) : base + e0 + e;
+      s_idx[e] = indices[src];
+      s_cnt[e] = counts != nullptr ? (float)counts[src] : (float)wvals[src];
     }
     __syncthreads();
     int e = 0;
@@ -172,7 +191,7 @@ static int pool_impl(const float* feat, int n_img, int C, int fh, int fw, const 
   SPALIGN_REQUIRE(threads <= 256 && threads * nacc == C4,
                   "pool: unsupported channel count %d", C);
 #define LAUNCH(N)                                                                              \
-  pool_rows_kernel<N><<<grid, threads, 0, stream>>>(feat, C, ncell, sp_off, indptr, indices,   \
+  pool_rows_kernel<N><<<grid, threads, 0, stream>>>(feat, C, ncell, fw, sp_off, indptr, indices, \
                                                     counts, wvals, area, sum_y, sum_x,         \
                                                     append_pos, out, ld_out)
   if (nacc == 1) LAUNCH(1);

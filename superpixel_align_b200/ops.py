@@ -23,7 +23,8 @@ LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 # kernel launches per entry point (kept in sync with csrc/*.cu)
 _LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
                     kmeans_sweep=1, kmeans_finish=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
-                    refine=2, confusion2=1, slic=0, sample_anchors=1, anchor_weights=1)
+                    refine=2, confusion2=1, slic=0, sample_anchors=1, anchor_weights=1,
+                    resize_nearest=1)
 
 
 def _count(name):
@@ -781,6 +782,21 @@ def refine(ov: Overlap, road_cell: torch.Tensor, thr: float):
         _ptr(keep), _stream()), 'refine')
     _count('refine')
     return overlap, road_px, keep
+
+
+def resize_nearest_u8(maps: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """uint8 / bool maps [n, h, w] -> [n, H, W] with cv2.INTER_NEAREST index arithmetic (the
+    resize to the label shape at batch_spalign_kmeans.py:470-477)."""
+    _require_cuda(maps)
+    m = maps.to(torch.uint8).contiguous()
+    n, h, w = m.shape
+    if (h, w) == (H, W):
+        return m
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=m.device)
+    check(_lib.load().spalign_resize_nearest_u8(_ptr(m), n, h, w, _ptr(out), int(H), int(W),
+                                                _stream()), 'resize_nearest_u8')
+    _count('resize_nearest')
+    return out
 
 
 def confusion2(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:

@@ -463,6 +463,17 @@ def test_refine_matches_mask_loop(ops):
             assert np.array_equal(refined[i].cpu().numpy(), want)
 
 
+@pytest.mark.parametrize('h,w,H,W', [(128, 256, 1024, 2048), (28, 28, 224, 224), (28, 28, 1024, 2048),
+                                     (224, 224, 100, 333), (1024, 2048, 224, 224), (37, 53, 37, 53)])
+def test_resize_nearest_matches_cv2(ops, h, w, H, W):
+    cv2 = pytest.importorskip('cv2')
+    rs = np.random.RandomState(h + W)
+    src = rs.randint(0, 5, size=(2, h, w)).astype(np.uint8)
+    got = ops.resize_nearest_u8(torch.from_numpy(src).to(dev()), H, W).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(got[i], cv2.resize(src[i], (W, H), interpolation=cv2.INTER_NEAREST))
+
+
 def test_confusion_matches_oracle(ops):
     rs = np.random.RandomState(3)
     gt = rs.randint(-1, 2, size=(3, 40, 50)).astype(np.int32)
