@@ -77,7 +77,7 @@ def _worker(rank, world, port, q, exchange, case):
         if not torch.equal(cen, ref):
             why.append('centres differ between ranks')
         ok = not why
-        msgs.append('%s/%s world %d: %d iterations, %.1f ms wall incl. init' %
+        msgs.append('%s/%s world %d: %d iterations, %.1f ms wall incl. host init and communicator set-up' %
                     (case, exchange, world, info['iters'], dt * 1e3))
         q.put((rank, 'ok' if ok else '; '.join(why), msgs))
     except Exception as e:  # pragma: no cover
