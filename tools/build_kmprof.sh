@@ -4,9 +4,10 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/ab /tmp/kmprof
-for f in overlap pool paint kmeans; do
+for s in superpixel_align_b200/csrc/*.cu; do
+  f=$(basename $s .cu)
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DKM_PROFILE \
-    -I include -c superpixel_align_b200/csrc/$f.cu -o /tmp/kmprof/$f.o &
+    -I include -c $s -o /tmp/kmprof/$f.o &
 done
 wait
-nvcc -shared -o tools/ab/lib_kmprof.so /tmp/kmprof/*.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/ab/lib_kmprof.so /tmp/kmprof/*.o
