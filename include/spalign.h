@@ -251,23 +251,6 @@ int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode,
                           double* totals, double* centers, int32_t* iters, int32_t* status,
                           float* ub, float* lb, double* cdelta, int slice_iters, int rows_per_set,
                           spalign_stream_t stream);
-/* spalign_kmeans_finish with K4 folded into it, for per-image clustering (group g == image g,
- * group_off == sp_off, int32 label maps, uint8 outputs): a CTA whose image has stopped paints it
- * (cluster_map[p] = assign[sp_off[g] + label[p]], road_mask = (== road_value); batch_spalign_kmeans.py
- * :193-199, :207) in tiles handed out by the atomic counters next_tile[G] (zero on entry), then
- * paints tiles of any other stopped image before it exits -- the SMs that idle while the slowest
- * images still iterate do the bandwidth-bound paint-back.  Nobody waits for anybody; whatever is
- * left (the images that stopped last) is painted by spalign_paint_rest with the same counters.
- * Output identical to spalign_paint. */
-int spalign_kmeans_finish_paint(const void* X, int x_dtype, int64_t ldx, const double* w, int D,
-                                int K, const int64_t* group_off, int G, int n_iter, int32_t* assign,
-                                double* totals, double* centers, int32_t* iters, int32_t* status,
-                                float* ub, float* lb, double* cdelta, const int32_t* labels,
-                                int64_t n_pix, uint8_t* cluster_map, uint8_t* road_mask,
-                                int road_value, int32_t* next_tile, spalign_stream_t stream);
-int spalign_paint_rest(const int32_t* labels, int n_img, int64_t n_pix, const int64_t* sp_off,
-                       const int32_t* table, uint8_t* cluster_map, uint8_t* road_mask,
-                       int road_value, int32_t* next_tile, spalign_stream_t stream);
 int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off, int G, int D,
                           int K, double* totals, spalign_stream_t stream);
 int spalign_kmeans_update(const double* totals, int G, int D, int K, int mode, int n_iter,

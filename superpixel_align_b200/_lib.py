@@ -54,9 +54,6 @@ SIGNATURES = {
     'spalign_comm_destroy': (_i, [_p]),
     'spalign_kmeans_finish': (_i, [_p, _i, _l, _i, _i, _l, _l, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _i, _i, _p]),
-    'spalign_kmeans_finish_paint': (_i, [_p, _i, _l, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
-                                         _p, _l, _p, _p, _i, _p, _p]),
-    'spalign_paint_rest': (_i, [_p, _i, _l, _p, _p, _p, _p, _i, _p, _p]),
     'spalign_kmeans_reduce': (_i, [_p, _p, _i, _i, _i, _p, _p]),
     'spalign_kmeans_update': (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     'spalign_kmeans_debug_stats': (_i, [C.POINTER(C.c_int64), _i]),

@@ -1668,7 +1668,6 @@ struct TailArgs {
   double* cdelta;            // [G][K]
   int n_iter;
   int slice;                 // iterations to run in this launch (0: until the group stops)
-  PaintJob paint;            // K4 for groups == images, done by CTAs as they run out of work
 };
 
 // Remaining iterations of one group by one persistent CTA (fp32 rows, after the first full
@@ -1684,12 +1683,9 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   KmSmem s;
   km_carve(&s, smem_raw, g.a.TR, g.a.srow, g.a.K, g.a.Dc, g.a.Kc, g.a.part_bytes, g.a.buf_rows);
   const int grp = blockIdx.x;
-  const int t = threadIdx.x;
-  const bool was_running = g.status[grp] == SPALIGN_KM_RUNNING;
-  if (!was_running && g.paint.labels == nullptr) return;
-  int status = SPALIGN_KM_ITER_CAP;
-  if (was_running) {  // ---- the iterations (body not re-indented) ----
+  if (g.status[grp] != SPALIGN_KM_RUNNING) return;
   const int64_t r0 = g.group_off[grp], r1 = g.group_off[grp + 1];
+  const int t = threadIdx.x;
   const int K = g.a.K, D = g.a.D, Dr = g.a.Dr, Dc = g.a.Dc;
   const size_t pv = (size_t)K * (D + 2) + 1;
   double* tt = g.totals + (size_t)grp * pv;
@@ -1703,6 +1699,7 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
   }
   __syncthreads();
   int it = g.iters[grp];
+  int status = SPALIGN_KM_ITER_CAP;
 #ifdef KM_PROFILE
   if (t == 0 && grp < 1024) {
     unsigned long long ns;
@@ -1927,12 +1924,9 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
     const int k = i / D, d = i - k * D;
     cg[i] = s.cen[(size_t)k * Dc + d];
   }
-  __threadfence();   // this CTA's assignment stores are visible before the status says "stopped"
-  __syncthreads();
   if (t == 0) {
     g.iters[grp] = it;
-    __threadfence();
-    *reinterpret_cast<volatile int32_t*>(&g.status[grp]) = status;
+    g.status[grp] = status;
 #ifdef KM_PROFILE
     if (grp < 1024) {
       unsigned long long ns;
@@ -1941,35 +1935,6 @@ __global__ void __launch_bounds__(KM_THREADS, MINB) kmeans_tail_kernel(TailArgs 
       g_km_trace[grp * 3 + 2] = (unsigned long long)it;
     }
 #endif
-  }
-  } else {
-    status = g.status[grp];
-  }
-  // ---- K4 epilogue: paint this image, then any image that has stopped and still has tiles.
-  // Nobody waits for anybody (a CTA that finds no tile exits), so CTAs not yet resident cannot
-  // be starved; what is left when the kernel ends is painted by spalign_paint_rest. ----
-  if (g.paint.labels != nullptr && status != SPALIGN_KM_RUNNING) {
-    __shared__ int s_tile;
-    paint_image_tiles(g.paint, grp, &s_tile);
-    const int G = g.paint.n_img;
-    const int n_tiles = (int)((g.paint.n_pix + PAINT_TILE - 1) / PAINT_TILE);
-    bool found = true;
-    while (found) {
-      found = false;
-      for (int h = 1; h < G; ++h) {
-        const int other = grp + h < G ? grp + h : grp + h - G;
-        __shared__ int s_go;
-        __syncthreads();
-        if (t == 0) {
-          const int st = *reinterpret_cast<volatile const int32_t*>(&g.status[other]);
-          const int nx = *reinterpret_cast<volatile const int32_t*>(&g.paint.next_tile[other]);
-          s_go = (st != SPALIGN_KM_RUNNING && nx < n_tiles) ? 1 : 0;
-          if (s_go) __threadfence();
-        }
-        __syncthreads();
-        if (s_go && paint_image_tiles(g.paint, other, &s_tile) > 0) found = true;
-      }
-    }
   }
 }
 
@@ -2367,12 +2332,13 @@ extern "C" int spalign_kmeans_iterate_dist(const void* X, int x_dtype, int64_t l
                              static_cast<cudaStream_t>(stream_));
 }
 
-static int kmeans_finish_impl(const void* X, int x_dtype, int64_t ldx, int pos_mode, int pos_w,
-                              int64_t pos_period, int64_t pos_row0, const double* w, int D, int K,
-                              const int64_t* group_off, int G, int n_iter, int32_t* assign,
-                              double* totals, double* centers, int32_t* iters, int32_t* status,
-                              float* ub, float* lb, double* cdelta, int slice_iters,
-                              int rows_per_set, const PaintJob* paint, spalign_stream_t stream_) {
+extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode,
+                                     int pos_w, int64_t pos_period, int64_t pos_row0,
+                                     const double* w, int D, int K, const int64_t* group_off,
+                                     int G, int n_iter, int32_t* assign, double* totals,
+                                     double* centers, int32_t* iters, int32_t* status, float* ub,
+                                     float* lb, double* cdelta, int slice_iters,
+                                     int rows_per_set, spalign_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SPALIGN_REQUIRE(group_off && assign && totals && centers && iters && status && ub && lb &&
                       cdelta && G > 0 && n_iter >= 0 && slice_iters >= 0 &&
@@ -2400,38 +2366,8 @@ static int kmeans_finish_impl(const void* X, int x_dtype, int64_t ldx, int pos_m
                   ? Dr % (2 * KM_THREADS) : 0;
   g.group_off = group_off; g.assign = assign; g.totals = totals; g.centers = centers;
   g.iters = iters; g.status = status; g.cdelta = cdelta; g.n_iter = n_iter; g.slice = slice_iters;
-  memset(&g.paint, 0, sizeof(g.paint));
-  if (paint != nullptr) g.paint = *paint;
   KM_DISPATCH(kmeans_tail_kernel, g, G);
   return check_launch("kmeans_finish");
-}
-
-extern "C" int spalign_kmeans_finish(const void* X, int x_dtype, int64_t ldx, int pos_mode,
-                                     int pos_w, int64_t pos_period, int64_t pos_row0,
-                                     const double* w, int D, int K, const int64_t* group_off,
-                                     int G, int n_iter, int32_t* assign, double* totals,
-                                     double* centers, int32_t* iters, int32_t* status, float* ub,
-                                     float* lb, double* cdelta, int slice_iters,
-                                     int rows_per_set, spalign_stream_t stream_) {
-  return kmeans_finish_impl(X, x_dtype, ldx, pos_mode, pos_w, pos_period, pos_row0, w, D, K,
-                            group_off, G, n_iter, assign, totals, centers, iters, status, ub, lb,
-                            cdelta, slice_iters, rows_per_set, nullptr, stream_);
-}
-
-extern "C" int spalign_kmeans_finish_paint(
-    const void* X, int x_dtype, int64_t ldx, const double* w, int D, int K,
-    const int64_t* group_off, int G, int n_iter, int32_t* assign, double* totals, double* centers,
-    int32_t* iters, int32_t* status, float* ub, float* lb, double* cdelta, const int32_t* labels,
-    int64_t n_pix, uint8_t* cluster_map, uint8_t* road_mask, int road_value, int32_t* next_tile,
-    spalign_stream_t stream_) {
-  SPALIGN_REQUIRE(labels && next_tile && (cluster_map || road_mask) && n_pix > 0,
-                  "kmeans_finish_paint: bad paint arguments");
-  PaintJob pj;
-  pj.labels = labels; pj.sp_off = group_off; pj.table = assign; pj.cluster_map = cluster_map;
-  pj.road_mask = road_mask; pj.next_tile = next_tile; pj.n_pix = n_pix; pj.n_img = G;
-  pj.road_value = road_value;
-  return kmeans_finish_impl(X, x_dtype, ldx, 0, 0, 0, 0, w, D, K, group_off, G, n_iter, assign,
-                            totals, centers, iters, status, ub, lb, cdelta, 0, 0, &pj, stream_);
 }
 
 extern "C" int spalign_kmeans_reduce(const double* partials, const int32_t* group_chunk_off,

@@ -198,31 +198,6 @@ extern "C" int spalign_paint(const void* labels, int label_dtype, int n_img, int
   return check_launch("paint");
 }
 
-// What the finish kernel's CTAs did not get to (images that stopped last): the same tile
-// counters, a few blocks per image; images already painted cost one atomic per block.
-__global__ void __launch_bounds__(256) paint_rest_kernel(PaintJob pj) {
-  __shared__ int s_tile;
-  paint_image_tiles(pj, blockIdx.y, &s_tile);
-}
-
-extern "C" int spalign_paint_rest(const int32_t* labels, int n_img, int64_t n_pix,
-                                  const int64_t* sp_off, const int32_t* table,
-                                  uint8_t* cluster_map, uint8_t* road_mask, int road_value,
-                                  int32_t* next_tile, spalign_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SPALIGN_REQUIRE(labels && sp_off && table && next_tile && (cluster_map || road_mask) &&
-                      n_img > 0 && n_img <= 65535 && n_pix > 0,
-                  "paint_rest: bad arguments");
-  PaintJob pj;
-  pj.labels = labels; pj.sp_off = sp_off; pj.table = table; pj.cluster_map = cluster_map;
-  pj.road_mask = road_mask; pj.next_tile = next_tile; pj.n_pix = n_pix; pj.n_img = n_img;
-  pj.road_value = road_value;
-  const int n_tiles = (int)((n_pix + PAINT_TILE - 1) / PAINT_TILE);
-  const int bx = n_tiles < 16 ? n_tiles : 16;
-  paint_rest_kernel<<<dim3(bx, n_img), 256, 0, stream>>>(pj);
-  return check_launch("paint_rest");
-}
-
 extern "C" int spalign_refine(const int64_t* sp_off, int n_img, int64_t n_rows, int ncell,
                               int max_rows_per_image, const int32_t* indptr,
                               const int32_t* indices, const int32_t* counts,

@@ -22,7 +22,7 @@ LAUNCHES = 0  # kernels launched by this library (bench.py reports it)
 
 # kernel launches per entry point (kept in sync with csrc/*.cu)
 _LAUNCH_COST = dict(label_max=1, overlap_csr=7, overlap_bilinear_csr=7, pool_weighted=1, pool=1, nchw_to_cellmajor=1, kmeans_groups=1,
-                    kmeans_sweep=1, kmeans_finish=1, paint_rest=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
+                    kmeans_sweep=1, kmeans_finish=1, kmeans_reduce=1, kmeans_update=1, kmeans_init=1, paint=1,
                     refine=2, confusion2=1, slic=0, sample_anchors=1, anchor_weights=1,
                     resize_nearest=1)
 
@@ -459,7 +459,7 @@ class KMeansLarge:
     def __init__(self, X, w, init_assign, K, group_off_host, n_iter=1000, pos_grid=None,
                  pos_row0=0, chunks_per_group=None, allreduce=None, fused=True,
                  incremental=True, bounds=True, tail=True, tail_after=1, tail_slice=0,
-                 comm=None, paint=None):
+                 comm=None):
         _require_cuda(X, w, init_assign)
         self.X = as_kmeans_rows(X)
         self.code, _ = _x_code(self.X)
@@ -507,11 +507,6 @@ class KMeansLarge:
                       (max_rows <= 8 * self.TAIL_ROWS and self.G >= 148)))
         self.tail_after = tail_after
         self.tail_slice = tail_slice
-        # K4 folded into the finish kernel: paint = dict(labels int32 [G, H, W], cluster_map /
-        # road_mask uint8 [G, H, W] or None, road_value); only when every group is one image
-        self.paint = paint if (paint is not None and self.tail and not tail_slice and
-                               not self.pos_mode) else None
-        self.painted = False
         if self.tail:
             self.goff_dev = torch.from_numpy(self.goff).to(dev, non_blocking=True)
         self._lib = _lib.load()
@@ -634,26 +629,6 @@ class KMeansLarge:
             plan = [(0, 4)]
             if self.tail_slice > 0:
                 plan = [(self.tail_slice, 2), (0, 4)]
-            if self.paint is not None:
-                pj = self.paint
-                lab = pj['labels']
-                n_pix = lab.shape[1] * lab.shape[2]
-                nxt = torch.zeros(self.G, dtype=torch.int32, device=self.dev)
-                check(self._lib.spalign_kmeans_finish_paint(
-                    _ptr(self.X), self.code, self.X.stride(0), _ptr(self.w), self.D, self.K,
-                    _ptr(self.goff_dev), self.G, self.n_iter, _ptr(self.assign), _ptr(self.totals),
-                    _ptr(self.centers), _ptr(self.iters), _ptr(self.status), _ptr(self.ub),
-                    _ptr(self.lb), _ptr(self.cdelta), _ptr(lab), n_pix, _ptr(pj.get('cluster_map')),
-                    _ptr(pj.get('road_mask')), int(pj.get('road_value', 0)), _ptr(nxt), _stream()),
-                    'kmeans_finish_paint')
-                _count('kmeans_finish')
-                check(self._lib.spalign_paint_rest(
-                    _ptr(lab), self.G, n_pix, _ptr(self.goff_dev), _ptr(self.assign),
-                    _ptr(pj.get('cluster_map')), _ptr(pj.get('road_mask')),
-                    int(pj.get('road_value', 0)), _ptr(nxt), _stream()), 'paint_rest')
-                _count('paint_rest')
-                self.painted = True
-                return KMeansResult(self.assign, self.iters, self.status, self.centers)
             for slice_iters, rows in plan:
                 check(self._lib.spalign_kmeans_finish(
                     _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,

@@ -71,7 +71,7 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
               images_per_group: int = 1, n_iter: int = 1000,
               nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8,
               timers: Optional[dict] = None, kmeans_impl: str = 'chunks',
-              out=None, fuse_paint: bool = True) -> PipelineOutput:
+              out=None) -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
     1 = per-image clustering).  Groups of more than 2048 rows use the multi-CTA k-means whose
@@ -113,33 +113,12 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
     mark('init', True)
     init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
     mark('init', False)
-    # per-image clustering of int32 maps into uint8 outputs: K4 rides in the finish kernel (CTAs
-    # whose image has stopped paint it and help with other stopped images while the slowest
-    # images still iterate); the 'paint' stage below is then only the leftover launch
-    fused = None
-    painted = False
-    if fuse_paint and images_per_group == 1 and kmeans_impl != 'groups' and \
-            labels.dtype == torch.int32 and out_dtype == torch.uint8 and labels.is_contiguous():
-        if out is not None:
-            cmap, mask = out
-        else:
-            cmap = torch.empty((n,) + tuple(labels.shape[1:]), dtype=torch.uint8, device=dev)
-            mask = torch.empty_like(cmap)
-        if cmap is not None and cmap.is_contiguous() and (mask is None or mask.is_contiguous()):
-            fused = dict(labels=labels, cluster_map=cmap, road_mask=mask, road_value=0)
     mark('kmeans', True)
     if kmeans_impl == 'groups':
         res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
     else:  # many CTAs per group; small groups finish in one persistent CTA each
-        km = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter, paint=fused)
-        res = km.run()
-        painted = km.painted
+        res = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter).run()
     mark('kmeans', False)
-    if painted:
-        mark('paint', True)
-        mark('paint', False)
-        return PipelineOutput(fused['cluster_map'], fused['road_mask'], res.assign, feats, weights,
-                              res.iters, res.status, m, ov, group_off_host, m_exp)
     mark('paint', True)
     cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype, out=out)
     mark('paint', False)

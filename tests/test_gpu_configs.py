@@ -121,34 +121,3 @@ def test_direct_clustering_full_feature_map():
     want = so.kmeans(4, X, prior, verbose=False)
     assert np.array_equal(cres.reshape(-1), np.asarray(want).astype(np.int32))
     assert road.sum() > 0
-
-
-@pytest.mark.parametrize('H,W,fh,fw,gy,gx,n', [(256, 512, 32, 64, 8, 12, 5), (64, 128, 8, 16, 4, 6, 7),
-                                               (33, 47, 33, 47, 3, 3, 3), (1024, 2048, 128, 256, 25, 40, 3)])
-def test_paint_fused_into_finish_kernel_equals_separate_paint(H, W, fh, fw, gy, gx, n):
-    """K4 inside the k-means finish kernel (tile stealing) + the leftover launch == spalign_paint."""
-    import numpy as np
-    import torch
-    from superpixel_align_b200 import pipeline, synth
-    dev = torch.device('cuda', 0)
-    labels = torch.from_numpy(np.stack([synth.voronoi_labels(H, W, gy, gx, image_index=20 + i)
-                                        for i in range(n)])).to(dev)
-    C = 16
-    feats = torch.from_numpy(np.stack([synth.smooth_features(C, fh, fw, seed=i).reshape(C, -1).T
-                                       for i in range(n)]).copy()).to(dev)
-    n_sp = [gy * gx] * n
-    np.random.seed(7)
-    a = pipeline.run_batch(labels, feats, n_sp, fh, fw, fuse_paint=True)
-    np.random.seed(7)
-    b = pipeline.run_batch(labels, feats, n_sp, fh, fw, fuse_paint=False)
-    torch.cuda.synchronize()
-    assert torch.equal(a.assign, b.assign) and torch.equal(a.iters, b.iters)
-    assert torch.equal(a.cluster_map, b.cluster_map) and torch.equal(a.road_mask, b.road_mask)
-    # into caller-provided slices, and with zero iterations allowed (every group stops at once)
-    cm = torch.zeros((n, H, W), dtype=torch.uint8, device=dev)
-    rm = torch.zeros_like(cm)
-    np.random.seed(7)
-    c = pipeline.run_batch(labels, feats, n_sp, fh, fw, out=(cm, rm), n_iter=1)
-    np.random.seed(7)
-    d = pipeline.run_batch(labels, feats, n_sp, fh, fw, n_iter=1, fuse_paint=False)
-    assert torch.equal(cm, d.cluster_map) and torch.equal(rm, d.road_mask) and c.cluster_map is cm
