@@ -366,7 +366,9 @@ def run_ours(args):
     # ---- inputs, resident in HBM ----
     t_setup = time.time()
     labels = synth.voronoi_labels_torch(max(n_img, 1), H, W, GY, GX, first_index=lo, device=dev)[:n_img]
-    model = drn.drn_c_26(device=dev, fold_bn=True)   # inference form: BatchNorm folded into the convs
+    # inference form of the input producer: BatchNorm folded, conv + bias (+ shortcut) + ReLU
+    # as single cuDNN calls
+    model = drn.drn_c_26(device=dev, fold_bn=True, fused=True)
     feats = torch.empty((n_img, FH * FW, C), dtype=torch.float32, device=dev)
     bs = 2
     for i in range(0, n_img, bs):
@@ -868,7 +870,8 @@ def run_e2e_images(args, ctx, model, labels, first_index):
             'h2d_bytes_per_step': ip.h2d_bytes // steps, 'd2h_bytes_per_step': ip.d2h_bytes // steps,
             'images_per_step': n_e2e, 'steps': steps, 'sub_batch': sub,
             'backbone_ms_per_image': float(np.mean(bb)) if bb else None,
-            'backbone': 'DRN-C-26 (random init, BatchNorm folded), fp32 / TF32 convolutions, channels_last, cuDNN',
+            'backbone': 'DRN-C-26 (random init; inference form: BatchNorm folded, conv+bias(+shortcut)+ReLU '
+                        'fused cuDNN calls), fp32 / TF32 convolutions, channels_last',
             'h2d_GBps_per_gpu': ip.h2d_bytes / dt / 1e9,
             'api': 'superpixel_align_b200.pipeline.ImagePipeline.process: pinned host uint8 '
                    '[b,3,H,W] images + uint16 label maps in, DRN + K1..K4 on the device, uint8 '

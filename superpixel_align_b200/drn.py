@@ -106,7 +106,46 @@ def fold_batchnorm(model):
     return model
 
 
-def drn_c_26(seed=1111, device='cuda', channels_last=True, fold_bn=False):
+class FusedDRN(nn.Module):
+    """Inference form of a BatchNorm-folded DRNC26 for CUDA: every conv + bias + ReLU is one cuDNN
+    call (``torch.cudnn_convolution_relu``) and the tail of a residual block -- conv + bias +
+    shortcut + ReLU -- is one ``torch.cudnn_convolution_add_relu``.  Same function as the module it
+    wraps (up to the convolution algorithm's rounding); removes the separate element-wise passes
+    over the full-resolution activation maps."""
+
+    def __init__(self, folded: DRNC26):
+        super().__init__()
+        self.m = folded
+
+    @staticmethod
+    def _cr(x, conv):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding,
+                                            conv.dilation, conv.groups)
+
+    @staticmethod
+    def _car(x, conv, z):
+        return torch.cudnn_convolution_add_relu(x, conv.weight, z, 1.0, conv.bias, conv.stride,
+                                                conv.padding, conv.dilation, conv.groups)
+
+    def forward(self, x, out_middle=False):
+        x = self._cr(x, self.m.stem[0])
+        maps = []
+        for st in self.m.stages:
+            for blk in st:
+                c1, c2 = blk.body[0], blk.body[2]
+                y = self._cr(x, c1)
+                if blk.residual:
+                    z = x if blk.proj is None else torch.nn.functional.conv2d(
+                        x, blk.proj[0].weight, blk.proj[0].bias, blk.proj[0].stride,
+                        blk.proj[0].padding, blk.proj[0].dilation)
+                    x = self._car(y, c2, z)
+                else:
+                    x = self._cr(y, c2)
+            maps.append(x)
+        return (x, maps) if out_middle else x
+
+
+def drn_c_26(seed=1111, device='cuda', channels_last=True, fold_bn=False, fused=False):
     torch.manual_seed(seed)
     m = DRNC26().eval()
     if fold_bn:
@@ -116,4 +155,7 @@ def drn_c_26(seed=1111, device='cuda', channels_last=True, fold_bn=False):
         m = m.to(memory_format=torch.channels_last)
     for p in m.parameters():
         p.requires_grad_(False)
+    if fused:
+        assert fold_bn, 'the fused inference form needs the BatchNorms folded'
+        m = FusedDRN(m)
     return m

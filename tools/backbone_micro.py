@@ -11,9 +11,12 @@ from superpixel_align_b200 import drn
 
 dev = torch.device('cuda', 0)
 model = drn.drn_c_26(device=dev)
+folded = drn.drn_c_26(device=dev, fold_bn=True)
+fused = drn.drn_c_26(device=dev, fold_bn=True, fused=True)
+MODELS = {'plain': model, 'folded_bn': folded, 'fused_conv_relu': fused}
 
 
-def run(b, dtype, bench, reps=4):
+def run(b, dtype, bench, reps=4, model=model):
     torch.backends.cudnn.benchmark = bench
     x = torch.randn((b, 3, 1024, 2048), device=dev).contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
@@ -37,8 +40,16 @@ def run(b, dtype, bench, reps=4):
     return e0.elapsed_time(e1) / reps / b
 
 
-for bench in (False, True):
-    for b in (2, 4, 8):
+x = torch.randn((2, 3, 256, 512), device=dev).contiguous(memory_format=torch.channels_last)
+with torch.no_grad():
+    ref = model(x)
+    for name, mm in MODELS.items():
+        print('%s: max abs diff vs plain %.3e (max abs %.3e)' % (name, (mm(x) - ref).abs().max().item(), ref.abs().max().item()))
+for name, mm in MODELS.items():
+    for b in (4, 8):
+        print('%s batch=%d fp32/tf32: %.2f ms/image' % (name, b, run(b, None, False, model=mm)))
+for bench in (False,):
+    for b in (8,):
         for dtype in (None, torch.bfloat16):
             try:
                 ms = run(b, dtype, bench)
