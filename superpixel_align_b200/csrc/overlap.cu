@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(256)
 rowsort_warp_kernel(OverlapWs ws, int* indptr, int64_t R, int* indices,
                     int* counts, int* area, double* sum_prior, double* wvals,
                     const int64_t* __restrict__ nnz_flags, int ncell_hint) {
+  __shared__ unsigned s_keys[8][64];
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
   const int lane = lane_id();
@@ -1184,6 +1185,293 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
              (unsigned long long)SPALIGN_F_LABEL_RANGE);
 }
 
+// ------------------------------------------------------------------------------------------
+// emit v3: the same bucket contract as v2, but the label passes run at full SIMD width.
+//
+// In v2 every lane walks the distinct labels of its own cell; 68 % of the cells hold one label,
+// so most lanes of a warp idle while a few make their second, third, fourth pass (≈1100
+// warp-instructions per 32 cells).  Here a warp splits the work:
+//   phase A  (every cell, converged): the 64 labels of the lane's cell are loaded straight into
+//            registers (16 x 128-bit loads in flight per lane) and folded into one word, OR of
+//            (label ^ first label): zero = uniform cell -> one pair with closed-form sums.  Mixed
+//            cells are pushed onto the warp's queue in shared memory (ballot + prefix popcount).
+//   phase B  (whenever the queue holds 32 cells, and once at the end for the rest): every lane
+//            takes one queued cell, re-reads its labels (L1 / L2 hits: DRAM traffic stays at
+//            1.07x the label bytes) and runs the label passes, all lanes busy for at least two.
+// No block barrier in the loop, no cross-warp traffic, no staging buffer.  Slot atomics never
+// stall the lane that issued them: a uniform pair's atomic is consumed after the NEXT cell's
+// loads have come back; the pairs of a mixed cell wait in shared memory, their atomics are issued
+// back to back when the cell is done and consumed when the lane starts its next mixed cell.
+// Measured alternatives (profiles/README.md): cp.async staging of the next cell, prefetch.L2 one
+// to three iterations ahead (evicted before use: DRAM traffic 1.5x), a queue of 16-bit label pairs
+// in shared memory with fp16x2 compares instead of the re-read -- all slower.
+#ifndef EMIT3_CELLS_PER_THREAD
+#define EMIT3_CELLS_PER_THREAD 16
+#endif
+#ifndef EMIT3_MIN_BLOCKS
+#define EMIT3_MIN_BLOCKS 4
+#endif
+constexpr int EMIT3_CELLS = EMIT3_CELLS_PER_THREAD;
+constexpr int EMIT3_ROWS = TILE_H * EMIT3_CELLS;  // cell rows per block
+constexpr int EMIT3_PEND = 4;
+
+constexpr size_t emit3_smem_bytes() {
+  return (size_t)EMIT3_PEND * (TILE_W * TILE_H) * 16                          // parked pairs
+         + (size_t)(TILE_W * TILE_H / 32) * 64 * sizeof(int)                  // warp queues
+         + (size_t)(TILE_W * 33 + EMIT3_ROWS * 9) * sizeof(double);           // prior tables
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(TILE_W * TILE_H, EMIT3_MIN_BLOCKS)
+emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
+                 const int64_t* __restrict__ sp_off, S8Ws ws, int64_t spill_cap,
+                 int64_t* nnz_flags, PriorTabs pt, const double* __restrict__ gy,
+                 bool have_prior) {
+  constexpr int NT = TILE_W * TILE_H, NWARP = NT / 32;
+  constexpr int PER_ROW = 8 * (int)sizeof(LabelT) / 16;  // 16-byte chunks per pixel row of a cell
+  extern __shared__ int4 s_dyn[];
+  int4 (*s_pend)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn);  // (row, packed, prior lo, hi)
+  int (*s_q)[64] = reinterpret_cast<int (*)[64]>(s_dyn + EMIT3_PEND * NT);
+  double (*s_T)[33] = reinterpret_cast<double (*)[33]>(s_dyn + EMIT3_PEND * NT + NWARP * 64 / 4);
+  double* s_gy = reinterpret_cast<double*>(s_T + TILE_W);  // [EMIT3_ROWS * 8] = gy of the rows
+  double* s_gy8 = s_gy + EMIT3_ROWS * 8;                   // [EMIT3_ROWS]
+  const int t = threadIdx.x, tx = t & (TILE_W - 1), ty = t / TILE_W;
+  const int lane = t & 31, wid = t >> 5;
+  const int img = blockIdx.z;
+  const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * EMIT3_ROWS;
+  const int cx = bx0 + tx;
+  const bool in_x = cx < fw;
+  const LabelT* limg = labels + (size_t)img * H * W;
+  const LabelT* pcol = limg + (size_t)cx * 8;
+  if (have_prior) {
+    // all loads first, then the stores: one round trip instead of one per loop iteration
+    constexpr int NTAB = (TILE_W * 33 + NT - 1) / NT, NGY = EMIT3_ROWS * 8 / NT;
+    double tab[NTAB], g[NGY], g8 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NTAB; ++i) {
+      const int e = t + i * NT, c = e / 33, k = e - c * 33, gc = bx0 + c;
+      tab[i] = 0.0;
+      if (e < TILE_W * 33 && gc < fw) tab[i] = k < 32 ? pt.gxT[(size_t)gc * 32 + k] : pt.gx8[gc];
+    }
+#pragma unroll
+    for (int i = 0; i < NGY; ++i) {
+      const int e = t + i * NT;
+      g[i] = (by0 * 8 + e < H) ? gy[by0 * 8 + e] : 0.0;
+    }
+    if (t < EMIT3_ROWS && by0 + t < fh) g8 = pt.gy8[by0 + t];
+#pragma unroll
+    for (int i = 0; i < NTAB; ++i) {
+      const int e = t + i * NT;
+      if (e < TILE_W * 33) s_T[e / 33][e % 33] = tab[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NGY; ++i) s_gy[t + i * NT] = g[i];
+    if (t < EMIT3_ROWS) s_gy8[t] = g8;
+  }
+  __syncthreads();  // the only block barrier: tables ready
+  const int64_t row0 = sp_off[img];
+  const int n_sp = (int)(sp_off[img + 1] - row0);
+  bool bad = false;
+  int npend = 0, pend_c = 0, ppos[EMIT3_PEND];  // parked pairs of the lane's last mixed cell
+
+  auto place_parked = [&]() {
+#pragma unroll
+    for (int k = 0; k < EMIT3_PEND; ++k)
+      if (k < npend) {
+        const int4 e = s_pend[k][t];
+        store_pair(ws, e.x, ppos[k], make_int4(pend_c, e.y, e.z, e.w), spill_cap, nnz_flags);
+      }
+    npend = 0;
+  };
+
+  // phase B: all label passes of one mixed cell (code = local cell row * 16 + local column)
+  auto mixed_cell = [&](int code) {
+    place_parked();
+    const int ly = code >> 4, lx = code & (TILE_W - 1);
+    const int cyy = by0 + ly, cxx = bx0 + lx;
+    const int c = cyy * fw + cxx;
+    const LabelT* p = limg + (size_t)cyy * 8 * W + (size_t)cxx * 8;
+    int v[64];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int h = 0; h < PER_ROW; ++h) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + h);
+        const int k = r * PER_ROW + h;
+        if (sizeof(LabelT) == 4) {
+          v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        } else {
+          const long long a = ((long long)q.y << 32) | (unsigned)q.x;
+          const long long b2 = ((long long)q.w << 32) | (unsigned)q.z;
+          v[2 * k] = (a >= 0 && a < n_sp) ? (int)a : -1;
+          v[2 * k + 1] = (b2 >= 0 && b2 < n_sp) ? (int)b2 : -1;
+        }
+      }
+    const double cell_prior = have_prior ? __dmul_rn(s_gy8[ly], s_T[lx][32]) : 0.0;
+    double emitted_prior = 0.0;
+    bool can_complement = true;
+    unsigned long long remaining = ~0ull;
+    int L = v[0];
+    while (true) {
+      unsigned lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        mask_or_eq(lo0, v[j], L, 1u << j);
+        mask_or_eq(lo1, v[j + 1], L, 2u << j);
+        mask_or_eq(hi0, v[32 + j], L, 1u << j);
+        mask_or_eq(hi1, v[33 + j], L, 2u << j);
+      }
+      const unsigned lo = lo0 | lo1, hi = hi0 | hi1;
+      const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      remaining &= ~m;
+      int nextl = 0;
+      if (remaining != 0ull) {
+        const int i = __ffsll((long long)remaining) - 1;
+        const LabelT nextq = __ldg(p + (size_t)(i >> 3) * W + (i & 7));
+        nextl = (sizeof(LabelT) == 4) ? (int)nextq
+                                      : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
+      }
+      if ((unsigned)L < (unsigned)n_sp) {
+        const int cnt = __popc(lo) + __popc(hi);
+        // bit i = pixel row i >> 3, column i & 7: sums of the offsets of the set bits
+        const int sxl = __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) +
+                        4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull);
+        const int syl = __popcll(m & 0xff00ff00ff00ff00ull) + 2 * __popcll(m & 0xffff0000ffff0000ull) +
+                        4 * __popcll(m & 0xffffffff00000000ull);
+        const int packed = cnt | (syl << 7) | (sxl << 15);
+        double pr = 0.0;
+        if (have_prior) {
+          if (remaining == 0ull && can_complement) {
+            // last label of the cell: whole-cell prior minus what the other labels took
+            pr = __dadd_rn(cell_prior, -emitted_prior);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned b = (r < 4 ? lo >> (8 * r) : hi >> (8 * (r - 4))) & 0xffu;
+              const double rs = __dadd_rn(s_T[lx][b & 15u], s_T[lx][16 + (b >> 4)]);
+              pr = __fma_rn(s_gy[ly * 8 + r], rs, pr);
+            }
+            emitted_prior = __dadd_rn(emitted_prior, pr);
+          }
+        }
+        if (npend == EMIT3_PEND) {  // more than EMIT3_PEND labels in one cell: place the oldest
+          const int4 e = s_pend[0][t];
+#pragma unroll
+          for (int k = 0; k + 1 < EMIT3_PEND; ++k) s_pend[k][t] = s_pend[k + 1][t];
+          --npend;
+          place_pair(ws, e.x, make_int4(c, e.y, e.z, e.w), spill_cap, nnz_flags);
+        }
+        s_pend[npend][t] = make_int4((int)(row0 + L), packed, __double2loint(pr),
+                                     __double2hiint(pr));
+        ++npend;
+      } else {  // label outside [0, n_sp): flag it, emit nothing
+        bad = true;
+        can_complement = false;
+      }
+      if (remaining == 0ull) break;
+      L = nextl;
+    }
+    pend_c = c;
+    // slot atomics of all pairs of the cell, back to back; consumed at the lane's next mixed cell
+#pragma unroll
+    for (int k = 0; k < EMIT3_PEND; ++k)
+      if (k < npend) ppos[k] = atomicAdd(&ws.cursor[s_pend[k][t].x], 1);
+  };
+
+  int qn = 0;         // cells in this warp's queue (warp-uniform)
+  bool upend = false;  // a uniform pair whose slot atomic is in flight
+  int upend_row = 0, upend_c = 0, upend_pos = 0;
+  double upend_prior = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < EMIT3_CELLS; ++it) {
+    const int ly = it * TILE_H + ty;
+    const int cy = by0 + ly;
+    if (by0 + it * TILE_H + 2 * wid >= fh) break;  // warp-uniform: both cell rows of the warp
+    const bool act = in_x && cy < fh;
+    int v0 = 0;
+    bool uniform = false, mixed = false;
+    if (act) {
+      const LabelT* p = pcol + (size_t)cy * 8 * W;
+      if (sizeof(LabelT) == 4) {
+        int4 q[16];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          q[2 * r] = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
+          q[2 * r + 1] = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + 1);
+        }
+        v0 = q[0].x;
+        unsigned diff = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          diff |= (unsigned)(q[k].x ^ v0) | (unsigned)(q[k].y ^ v0);
+          diff |= (unsigned)(q[k].z ^ v0) | (unsigned)(q[k].w ^ v0);
+        }
+        mixed = diff != 0;
+        uniform = !mixed && (unsigned)v0 < (unsigned)n_sp;
+      } else {
+        // 64-bit labels, two halves of the cell: a uniform cell is checked on the full value,
+        // cells with different out-of-range labels count as mixed (phase B flags them)
+        unsigned dlo = 0, dhi = 0;
+        int v0h = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int4 q[16];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              q[4 * r + h] =
+                  __ldg(reinterpret_cast<const int4*>(p + (size_t)(4 * half + r) * W) + h);
+          if (half == 0) { v0 = q[0].x; v0h = q[0].y; }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            dlo |= (unsigned)(q[k].x ^ v0) | (unsigned)(q[k].z ^ v0);
+            dhi |= (unsigned)(q[k].y ^ v0h) | (unsigned)(q[k].w ^ v0h);
+          }
+        }
+        mixed = (dlo | dhi) != 0;
+        uniform = !mixed && v0h == 0 && (unsigned)v0 < (unsigned)n_sp;
+      }
+      if (!mixed && !uniform) bad = true;
+    }
+    if (upend) {  // last iteration's uniform pair: its slot came back while the loads were out
+      store_pair(ws, upend_row, upend_pos,
+                 make_int4(upend_c, PACKED_FULL, __double2loint(upend_prior),
+                           __double2hiint(upend_prior)),
+                 spill_cap, nnz_flags);
+      upend = false;
+    }
+    const unsigned mb = __ballot_sync(0xffffffffu, mixed);
+    if (mixed) s_q[wid][qn + __popc(mb & ((1u << lane) - 1u))] = ly * TILE_W + tx;
+    qn += __popc(mb);
+    __syncwarp();
+    if (qn >= 32) {
+      qn -= 32;
+      const int code = s_q[wid][qn + lane];
+      __syncwarp();
+      mixed_cell(code);
+      __syncwarp();
+    }
+    if (uniform) {
+      upend_row = (int)(row0 + v0);
+      upend_c = cy * fw + cx;
+      upend_prior = have_prior ? __dmul_rn(s_gy8[ly], s_T[tx][32]) : 0.0;
+      upend_pos = atomicAdd(&ws.cursor[upend_row], 1);
+      upend = true;
+    }
+  }
+  if (upend)
+    store_pair(ws, upend_row, upend_pos,
+               make_int4(upend_c, PACKED_FULL, __double2loint(upend_prior),
+                         __double2hiint(upend_prior)),
+               spill_cap, nnz_flags);
+  if (lane < qn) mixed_cell(s_q[wid][lane]);
+  place_parked();
+  if (bad)
+    atomicOr(reinterpret_cast<unsigned long long*>(&nnz_flags[1]),
+             (unsigned long long)SPALIGN_F_LABEL_RANGE);
+}
+
 // spilled pairs (rows longer than a bucket) -> tail of their row segment
 __global__ void __launch_bounds__(256)
 spill_scatter_kernel(S8Ws ws, const int* __restrict__ indptr, int64_t nnz_cap,
@@ -1206,6 +1494,7 @@ __global__ void __launch_bounds__(256)
 rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int* counts,
                       int* area, int64_t* sum_y, int64_t* sum_x, double* sum_prior,
                       const int64_t* __restrict__ nnz_flags, int ncell, PriorTabs pt) {
+  __shared__ unsigned s_keys[8][64];
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
   const int lane = lane_id();
@@ -1230,11 +1519,46 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
   long long y_sum = 0, x_sum = 0;
   double ps = 0.0;
   if (L <= 64 && ncell <= (1 << 24)) {
-    // bitonic sort of (cell << 7 | slot) keys, two per lane (elements lane and lane + 32)
+    // keys (cell << 7 | slot), two per lane (elements lane and lane + 32), to be sorted by cell
     const unsigned PAD = 0xffffffffu;
-    unsigned k0 = lane < L ? ((unsigned)bk[lane].x << 7) | (unsigned)lane : PAD;
-    unsigned k1 = lane + 32 < L ? ((unsigned)bk[lane + 32].x << 7) | (unsigned)(lane + 32) : PAD;
-    if (L > 32) {
+    const int c0 = lane < L ? bk[lane].x : -1, c1 = lane + 32 < L ? bk[lane + 32].x : -1;
+    unsigned k0 = c0 >= 0 ? ((unsigned)c0 << 7) | (unsigned)lane : PAD;
+    unsigned k1 = c1 >= 0 ? ((unsigned)c1 << 7) | (unsigned)(lane + 32) : PAD;
+    // A superpixel is compact: its cells sit in a small bounding box.  Box of <= 256 cells (every
+    // row of a SLIC-like map): one bit per box cell, OR-reduced over the warp; the rank of a
+    // cell is the number of set bits below its own -- ~70 warp-instructions against the 435 of
+    // the 21-stage network below.
+    const int y0 = c0 / fw, x0 = c0 - y0 * fw, y1 = c1 / fw, x1 = c1 - y1 * fw;
+    const int big = 0x7fffffff;
+    const int ymin = __reduce_min_sync(0xffffffffu, min(c0 >= 0 ? y0 : big, c1 >= 0 ? y1 : big));
+    const int ymax = __reduce_max_sync(0xffffffffu, max(c0 >= 0 ? y0 : -1, c1 >= 0 ? y1 : -1));
+    const int xmin = __reduce_min_sync(0xffffffffu, min(c0 >= 0 ? x0 : big, c1 >= 0 ? x1 : big));
+    const int xmax = __reduce_max_sync(0xffffffffu, max(c0 >= 0 ? x0 : -1, c1 >= 0 ? x1 : -1));
+    const int wbox = xmax - xmin + 1, nbits = wbox * (ymax - ymin + 1);
+    if (nbits <= 256) {
+      const int b0 = c0 >= 0 ? (y0 - ymin) * wbox + (x0 - xmin) : -1;
+      const int b1 = c1 >= 0 ? (y1 - ymin) * wbox + (x1 - xmin) : -1;
+      int r0 = 0, r1 = 0;
+#pragma unroll
+      for (int wd = 0; wd < 8; ++wd) {
+        if (wd * 32 < nbits) {  // warp-uniform
+          const unsigned mine = ((b0 >> 5) == wd ? 1u << (b0 & 31) : 0u) |
+                                ((b1 >> 5) == wd ? 1u << (b1 & 31) : 0u);
+          const unsigned word = __reduce_or_sync(0xffffffffu, mine);
+          const int full = __popc(word);
+          r0 += (b0 >> 5) > wd ? full : ((b0 >> 5) == wd ? __popc(word & ((1u << (b0 & 31)) - 1u)) : 0);
+          r1 += (b1 >> 5) > wd ? full : ((b1 >> 5) == wd ? __popc(word & ((1u << (b1 & 31)) - 1u)) : 0);
+        }
+      }
+      // hand the keys to the lanes that own their sorted positions
+      unsigned* s_key = s_keys[warp_id()];
+      if (c0 >= 0) s_key[r0] = k0;
+      if (c1 >= 0) s_key[r1] = k1;
+      __syncwarp();
+      k0 = lane < L ? s_key[lane] : PAD;
+      k1 = lane + 32 < L ? s_key[lane + 32] : PAD;
+      __syncwarp();
+    } else if (L > 32) {
 #pragma unroll
       for (int k = 2; k <= 64; k <<= 1) {
 #pragma unroll
@@ -1511,24 +1835,43 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
     S8Ws w8;
     carve_s8(w8, aligned, fh, fw, n_rows, nnz_cap);
     init_s8_kernel<<<2 * kNumSMs, 256, 0, stream>>>(w8, fh, fw, gy, gx, nnz_flags);
-    dim3 egrid((fw + TILE_W - 1) / TILE_W,
-               (fh + TILE_H * EMIT_CELLS - 1) / (TILE_H * EMIT_CELLS), n_img);
     constexpr int NT = TILE_W * TILE_H;
     const PriorTabs pt{w8.gyT, fh, w8.gxT, w8.gx8, w8.gy8};
-    if (label_dtype == SPALIGN_I32) {
+    const char* emit_sel = getenv("SPALIGN_K1_EMIT");  // "2": round 2's one-lane-per-cell passes
+    if (emit_sel != nullptr && emit_sel[0] == '2') {
+      dim3 egrid((fw + TILE_W - 1) / TILE_W,
+                 (fh + TILE_H * EMIT_CELLS - 1) / (TILE_H * EMIT_CELLS), n_img);
       const size_t tab = (size_t)(TILE_W * 33 + EMIT_CELLS * TILE_H * 9) * sizeof(double);
-      const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4) + tab;
-      SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int32_t>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      emit_s8v2_kernel<int32_t><<<egrid, NT, smem, stream>>>(
-          (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
+      if (label_dtype == SPALIGN_I32) {
+        const size_t smem = (size_t)NT * ((16 + 4) * 16 + 4 * 4) + tab;
+        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int32_t>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_s8v2_kernel<int32_t><<<egrid, NT, smem, stream>>>(
+            (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
+      } else {
+        const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4) + tab;
+        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int64_t>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_s8v2_kernel<int64_t><<<egrid, NT, smem, stream>>>(
+            (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
+      }
     } else {
-      const size_t tab = (size_t)(TILE_W * 33 + EMIT_CELLS * TILE_H * 9) * sizeof(double);
-      const size_t smem = (size_t)NT * ((32 + 4) * 16 + 4 * 4) + tab;
-      SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v2_kernel<int64_t>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      emit_s8v2_kernel<int64_t><<<egrid, NT, smem, stream>>>(
-          (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
+      dim3 egrid((fw + TILE_W - 1) / TILE_W, (fh + EMIT3_ROWS - 1) / EMIT3_ROWS, n_img);
+      if (label_dtype == SPALIGN_I32) {
+        constexpr size_t smem = emit3_smem_bytes();
+        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v3_kernel<int32_t>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_s8v3_kernel<int32_t><<<egrid, NT, smem, stream>>>(
+            (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy,
+            gy != nullptr);
+      } else {
+        constexpr size_t smem = emit3_smem_bytes();
+        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v3_kernel<int64_t>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_s8v3_kernel<int64_t><<<egrid, NT, smem, stream>>>(
+            (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy,
+            gy != nullptr);
+      }
     }
     const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
     scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum);
