@@ -1489,6 +1489,17 @@ spill_scatter_kernel(S8Ws ws, const int* __restrict__ indptr, int64_t nnz_cap,
   }
 }
 
+// c / fw for 0 <= c < 2^24 without the ~20-instruction integer division: float quotient, then
+// one exact correction step
+__device__ __forceinline__ int div_cells(int c, int fw, float inv_fw, int& rem) {
+  int q = __float2int_rz(__int2float_rn(c) * inv_fw);
+  int r = c - q * fw;
+  if (r < 0) { --q; r += fw; }
+  if (r >= fw) { ++q; r -= fw; }
+  rem = r;
+  return q;
+}
+
 // one warp per row of <= BUCKET_CAP cells, straight out of the bucket
 __global__ void __launch_bounds__(256)
 rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int* counts,
@@ -1513,6 +1524,7 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
   }
   const int L = ws.cursor[r];
   if (L > BUCKET_CAP) return;
+  const float inv_fw = 1.0f / (float)fw;
   const int base = indptr[r];
   const int4* bk = ws.bucket + (size_t)r * BUCKET_CAP;
   int a_sum = 0;
@@ -1528,7 +1540,8 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
     // row of a SLIC-like map): one bit per box cell, OR-reduced over the warp; the rank of a
     // cell is the number of set bits below its own -- ~70 warp-instructions against the 435 of
     // the 21-stage network below.
-    const int y0 = c0 / fw, x0 = c0 - y0 * fw, y1 = c1 / fw, x1 = c1 - y1 * fw;
+    int x0, x1;
+    const int y0 = div_cells(max(c0, 0), fw, inv_fw, x0), y1 = div_cells(max(c1, 0), fw, inv_fw, x1);
     const int big = 0x7fffffff;
     const int ymin = __reduce_min_sync(0xffffffffu, min(c0 >= 0 ? y0 : big, c1 >= 0 ? y1 : big));
     const int ymax = __reduce_max_sync(0xffffffffu, max(c0 >= 0 ? y0 : -1, c1 >= 0 ? y1 : -1));
@@ -1539,9 +1552,9 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       const int b0 = c0 >= 0 ? (y0 - ymin) * wbox + (x0 - xmin) : -1;
       const int b1 = c1 >= 0 ? (y1 - ymin) * wbox + (x1 - xmin) : -1;
       int r0 = 0, r1 = 0;
-#pragma unroll
-      for (int wd = 0; wd < 8; ++wd) {
-        if (wd * 32 < nbits) {  // warp-uniform
+#pragma unroll 1
+      for (int wd = 0; wd * 32 < nbits; ++wd) {  // warp-uniform trip count (2 for SLIC-like maps)
+        {
           const unsigned mine = ((b0 >> 5) == wd ? 1u << (b0 & 31) : 0u) |
                                 ((b1 >> 5) == wd ? 1u << (b1 & 31) : 0u);
           const unsigned word = __reduce_or_sync(0xffffffffu, mine);
@@ -1591,7 +1604,8 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
     double pv1 = 0.0;
     if (lane < L) {
       const int4 e = bk[k0 & 127u];
-      const int cn = packed_cnt(e.y), cyy = e.x / fw, cxx = e.x - cyy * fw;
+      int cxx;
+      const int cn = packed_cnt(e.y), cyy = div_cells(e.x, fw, inv_fw, cxx);
       indices[base + lane] = e.x;
       counts[base + lane] = cn;
       a_sum = cn;
@@ -1602,7 +1616,8 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
     }
     if (lane + 32 < L) {
       const int4 e = bk[k1 & 127u];
-      const int cn = packed_cnt(e.y), cyy = e.x / fw, cxx = e.x - cyy * fw;
+      int cxx;
+      const int cn = packed_cnt(e.y), cyy = div_cells(e.x, fw, inv_fw, cxx);
       indices[base + lane + 32] = e.x;
       counts[base + lane + 32] = cn;
       a_sum += cn;
@@ -1644,13 +1659,33 @@ rowsort_bucket_kernel(S8Ws ws, int* indptr, int64_t R, int fw, int* indices, int
       for (int e = lane; e < L; e += 32) ps = __dadd_rn(ps, sorted_prior[base + e]);
     }
   }
+  if (L <= 64 && ncell <= (1 << 24)) {
+    // <= 4096 pixels per row and coordinates below 2^15 (ncell <= 2^24 cells of 8x8 pixels would
+    // allow 2^27 along one axis only for degenerate shapes; those take the general branch):
+    // the integer sums fit 32 bits, one REDUX each
+    const bool small = (long long)ncell / fw * 8 <= (1 << 19) && (long long)fw * 8 <= (1 << 19);
+    if (small) {
+      a_sum = (int)__reduce_add_sync(0xffffffffu, (unsigned)a_sum);
+      y_sum = (long long)__reduce_add_sync(0xffffffffu, (unsigned)y_sum);
+      x_sum = (long long)__reduce_add_sync(0xffffffffu, (unsigned)x_sum);
+    } else {
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
-    y_sum += __shfl_xor_sync(0xffffffffu, y_sum, d);
-    x_sum += __shfl_xor_sync(0xffffffffu, x_sum, d);
-    ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, d));
+      for (int d = 16; d > 0; d >>= 1) {
+        a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
+        y_sum += __shfl_xor_sync(0xffffffffu, y_sum, d);
+        x_sum += __shfl_xor_sync(0xffffffffu, x_sum, d);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a_sum += __shfl_xor_sync(0xffffffffu, a_sum, d);
+      y_sum += __shfl_xor_sync(0xffffffffu, y_sum, d);
+      x_sum += __shfl_xor_sync(0xffffffffu, x_sum, d);
+    }
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, d));
   if (lane == 0) {
     area[r] = a_sum;
     sum_y[r] = y_sum;

@@ -610,6 +610,42 @@ class KMeansLarge:
             self.init_centers()
         self._sweep(1)
 
+    def can_split(self) -> bool:
+        """True when the iterations after the first run in the per-group finish kernel, i.e. when
+        ``prepare()`` + ``finish_groups()`` over any partition of the groups equals ``run()``."""
+        return bool(self.tail and self.n_iter > 0)
+
+    def prepare(self):
+        """Seed centres (one sweep) and the first full iteration(s): leaves running sums, centres,
+        centre drift and Hamerly bounds for ``finish_groups``."""
+        if not self._init_done:
+            self.init_centers()
+        for _ in range(min(self.tail_after, self.n_iter)):
+            self._sweep(1)
+
+    def finish_groups(self, g0: int, g1: int):
+        """Remaining iterations of groups [g0, g1): one persistent CTA per group on the current
+        stream.  Groups are independent, so disjoint ranges may run on different streams (the
+        paint-back of a finished range can then start while slower ranges still iterate)."""
+        # default: one launch, one CTA per SM (4 rows per warp set).  tail_slice > 0 first runs
+        # that many iterations with every group resident (2 CTAs per SM, 2 rows per set), then
+        # the rest -- measured no faster at 300 groups (profiles/README.md)
+        plan = [(0, 4)]
+        if self.tail_slice > 0:
+            plan = [(self.tail_slice, 2), (0, 4)]
+        for slice_iters, rows in plan:
+            check(self._lib.spalign_kmeans_finish(
+                _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
+                self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K,
+                _ptr(self.goff_dev[g0:]), g1 - g0, self.n_iter, _ptr(self.assign),
+                _ptr(self.totals[g0:]), _ptr(self.centers[g0:]), _ptr(self.iters[g0:]),
+                _ptr(self.status[g0:]), _ptr(self.ub), _ptr(self.lb), _ptr(self.cdelta[g0:]),
+                slice_iters, rows, _stream()), 'kmeans_finish')
+            _count('kmeans_finish')
+
+    def result(self) -> KMeansResult:
+        return KMeansResult(self.assign, self.iters, self.status, self.centers)
+
     def run(self, poll: int = 4, first_poll: int = 6, blocking: bool = False,
             lookahead: int = 2) -> KMeansResult:
         """Iterate until every group has stopped.  The stop flags are read back asynchronously
@@ -618,27 +654,12 @@ class KMeansLarge:
         exit at once), so the GPU does not idle during the round trip.  When a read-back lands, finished groups are dropped from the chunk
         list.  ``blocking=True`` synchronises at every poll instead (deterministic launch
         count, used by tests)."""
+        if self.can_split():
+            self.prepare()
+            self.finish_groups(0, self.G)
+            return self.result()
         if not self._init_done:
             self.init_centers()
-        if self.tail and self.n_iter > 0:
-            for _ in range(min(self.tail_after, self.n_iter)):
-                self._sweep(1)
-            # default: one launch, one CTA per SM (4 rows per warp set).  tail_slice > 0 first
-            # runs that many iterations with every group resident (2 CTAs per SM, 2 rows per
-            # set), then the rest -- measured no faster at 300 groups (profiles/README.md)
-            plan = [(0, 4)]
-            if self.tail_slice > 0:
-                plan = [(self.tail_slice, 2), (0, 4)]
-            for slice_iters, rows in plan:
-                check(self._lib.spalign_kmeans_finish(
-                    _ptr(self.X), self.code, self.X.stride(0), self.pos_mode, self.pos_w,
-                    self.pos_period, self.pos_row0, _ptr(self.w), self.D, self.K,
-                    _ptr(self.goff_dev), self.G, self.n_iter, _ptr(self.assign),
-                    _ptr(self.totals), _ptr(self.centers), _ptr(self.iters), _ptr(self.status),
-                    _ptr(self.ub), _ptr(self.lb), _ptr(self.cdelta), slice_iters, rows,
-                    _stream()), 'kmeans_finish')
-                _count('kmeans_finish')
-            return KMeansResult(self.assign, self.iters, self.status, self.centers)
         if self.allreduce is not None:
             # every rank must enqueue the same number of collectives: poll at fixed iterations
             blocking = True

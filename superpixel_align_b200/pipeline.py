@@ -71,13 +71,16 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
               images_per_group: int = 1, n_iter: int = 1000,
               nnz_cap_per_image: Optional[int] = None, out_dtype=torch.uint8,
               timers: Optional[dict] = None, kmeans_impl: str = 'chunks',
-              out=None) -> PipelineOutput:
+              out=None, paint_overlap: int = 0) -> PipelineOutput:
     """One pass of the hot path over a batch.  ``images_per_group`` = the reference's
     ``--batchsize`` (superpixels of that many consecutive images are clustered jointly;
     1 = per-image clustering).  Groups of more than 2048 rows use the multi-CTA k-means whose
     driver polls a stop flag asynchronously; everything else is free of host synchronisation.
     Data-dependent conditions (overlap capacity, label range, empty rows, tied prior weights)
-    are left in device words: call ``.check()`` on the result at the next synchronisation."""
+    are left in device words: call ``.check()`` on the result at the next synchronisation.
+    ``paint_overlap`` = p > 1 cuts the groups into p ranges whose k-means finish kernels run on
+    separate streams; the paint-back of a range starts when that range has stopped, under the
+    tail of the slower ranges (same results; the 'kmeans' timer then includes the paint-back)."""
     n = labels.shape[0]
     n_sp = np.asarray(n_sp, dtype=np.int64)
 
@@ -114,19 +117,66 @@ def run_batch(labels: torch.Tensor, feat_cellmajor: torch.Tensor, n_sp: Sequence
     init, m = ops.kmeans_init_device(weights, goff, flat_d, off_d)
     mark('init', False)
     mark('kmeans', True)
+    km = None
     if kmeans_impl == 'groups':
         res = ops.kmeans_groups(feats, weights, init, k, goff, n_iter=n_iter)
     else:  # many CTAs per group; small groups finish in one persistent CTA each
-        res = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter).run()
-    mark('kmeans', False)
-    mark('paint', True)
-    cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype, out=out)
-    mark('paint', False)
+        km = ops.KMeansLarge(feats, weights, init, k, group_off_host, n_iter=n_iter)
+    n_groups = len(group_off_host) - 1
+    if km is not None and paint_overlap > 1 and km.can_split() and n_groups >= 2 * paint_overlap:
+        # The finish kernel ends with its slowest group while most SMs are already idle.  Ranges
+        # of groups finish on separate (high-priority) streams; the paint-back of a range starts
+        # on a low-priority stream as soon as that range is done and runs on the SMs the
+        # remaining groups do not occupy.  Same kernels, same results.
+        km.prepare()
+        cmap, mask = out if out is not None else (
+            torch.empty(labels.shape, dtype=out_dtype, device=dev),
+            torch.empty(labels.shape, dtype=torch.uint8, device=dev))
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        hi, lo = _paint_streams(dev, paint_overlap)
+        cuts = np.linspace(0, n_groups, paint_overlap + 1).astype(np.int64)
+        for j in range(paint_overlap):
+            g0, g1 = int(cuts[j]), int(cuts[j + 1])
+            i0, i1 = int(g_idx[g0]), int(g_idx[g1])
+            hi[j].wait_event(fork)
+            with torch.cuda.stream(hi[j]):
+                km.finish_groups(g0, g1)
+                done = torch.cuda.Event()
+                done.record(hi[j])
+            lo[j].wait_event(done)
+            with torch.cuda.stream(lo[j]):
+                ops.paint(labels[i0:i1], ov.sp_off[i0:i1 + 1], km.assign,
+                          out=(cmap[i0:i1], mask[i0:i1]))
+                painted = torch.cuda.Event()
+                painted.record(lo[j])
+            cur.wait_event(painted)
+        res = km.result()
+        mark('kmeans', False)   # includes the overlapped paint-back
+    else:
+        if km is not None:
+            res = km.run()
+        mark('kmeans', False)
+        mark('paint', True)
+        cmap, mask = ops.paint(labels, ov.sp_off, res.assign, out_dtype=out_dtype, out=out)
+        mark('paint', False)
     return PipelineOutput(cmap, mask, res.assign, feats, weights, res.iters, res.status, m, ov,
                           group_off_host, m_exp)
 
 
 _SIDE_STREAMS = {}
+_PAINT_STREAMS = {}
+
+
+def _paint_streams(dev, n):
+    """(high-priority streams for the k-means finish ranges, default-priority ones for their
+    paint-back), cached per device."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    if key not in _PAINT_STREAMS:
+        _PAINT_STREAMS[key] = ([torch.cuda.Stream(device=dev, priority=-1) for _ in range(n)],
+                               [torch.cuda.Stream(device=dev) for _ in range(n)])
+    return _PAINT_STREAMS[key]
 
 
 def _side_streams(dev, n):

@@ -203,6 +203,31 @@ def test_run_batch_overlapped_on_side_streams_equals_one_batch():
         assert len(out.parts) == -(-n // sb)
 
 
+def test_run_batch_paint_overlap_equals_sequential():
+    """Ranges of groups finishing on separate streams with their paint-back overlapped: same
+    cluster maps, masks, iteration counts and stop reasons as the one-stream form (per-image and
+    joint groups; ragged last range)."""
+    from superpixel_align_b200 import pipeline
+    d = torch.device('cuda', 0)
+    H, W, fh, fw, C = 128, 256, 16, 32, 32
+    n = 13
+    labs = torch.from_numpy(np.stack([synth.voronoi_labels(H, W, 6, 10, image_index=i) for i in range(n)])).to(d)
+    feats = torch.from_numpy(np.ascontiguousarray(np.stack(
+        [synth.smooth_features(C, fh, fw, seed=i).reshape(C, -1).T for i in range(n)]))).to(d)
+    for ipg in (1, 2):
+        np.random.seed(5)
+        ref = pipeline.run_batch(labs, feats, [60] * n, fh, fw, k=4, images_per_group=ipg)
+        for po in (2, 3):
+            np.random.seed(5)
+            out = pipeline.run_batch(labs, feats, [60] * n, fh, fw, k=4, images_per_group=ipg,
+                                     paint_overlap=po)
+            torch.cuda.synchronize()
+            assert torch.equal(out.cluster_map, ref.cluster_map)
+            assert torch.equal(out.road_mask, ref.road_mask)
+            assert torch.equal(out.iters, ref.iters) and torch.equal(out.status, ref.status)
+            assert torch.equal(out.assign, ref.assign)
+
+
 def test_results_scores_and_artefacts(tmp_path):
     from superpixel_align_b200 import results
     rs = np.random.RandomState(1)

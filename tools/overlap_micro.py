@@ -44,11 +44,17 @@ def timed(fn, reps=5):
 ms, ref = timed(lambda: pipeline.run_batch(labels, feats, n_sp, FH, FW))
 print('sequential          %.3f ms  (%.0f images/s)  iters mean %.1f max %d' %
       (ms, n / ms * 1e3, ref.iters.float().mean().item(), ref.iters.max().item()))
-for sb, ns in ((150, 2), (100, 2), (75, 2), (60, 2), (50, 2), (100, 3), (60, 3), (38, 2)):
-    if sb >= n:
-        continue
-    ms, out = timed(lambda: pipeline.run_batch_overlapped(labels, feats, n_sp, FH, FW, sub_batch=sb,
-                                                          n_streams=ns))
-    same = bool((out.cluster_map == ref.cluster_map).all()) and bool((out.iters == ref.iters).all())
-    print('overlapped sb=%3d streams=%d  %.3f ms  (%.0f images/s)  identical=%s' %
-          (sb, ns, ms, n / ms * 1e3, same))
+for po in (10, 12, 15, 20):
+    ms, out = timed(lambda: pipeline.run_batch(labels, feats, n_sp, FH, FW, paint_overlap=po))
+    same = bool((out.cluster_map == ref.cluster_map).all()) and bool((out.iters == ref.iters).all()) \
+        and bool((out.road_mask == ref.road_mask).all())
+    print('paint_overlap=%2d  %.3f ms  (%.0f images/s)  identical=%s' % (po, ms, n / ms * 1e3, same))
+if os.environ.get('OVERLAP_SUBBATCH'):
+  for sb, ns in ((150, 2), (50, 6), (30, 10), (20, 15), (20, 5), (50, 3)):
+      if sb >= n:
+          continue
+      ms, out = timed(lambda: pipeline.run_batch_overlapped(labels, feats, n_sp, FH, FW, sub_batch=sb,
+                                                            n_streams=ns))
+      same = bool((out.cluster_map == ref.cluster_map).all()) and bool((out.iters == ref.iters).all())
+      print('overlapped sb=%3d streams=%d  %.3f ms  (%.0f images/s)  identical=%s' %
+            (sb, ns, ms, n / ms * 1e3, same))
