@@ -1211,47 +1211,88 @@ emit_s8v2_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
 #ifndef EMIT3_MIN_BLOCKS
 #define EMIT3_MIN_BLOCKS 4
 #endif
+#ifndef EMIT3_PICK_TREE
+#define EMIT3_PICK_TREE 1
+#endif
+#ifndef EMIT3_TILE_W
+#define EMIT3_TILE_W 32
+#endif
+// cells per block: E3_W along x (one warp = 32 neighbouring cells = 1 KB of every pixel row) x E3_H
+constexpr int E3_W = EMIT3_TILE_W, E3_H = 128 / E3_W;
 constexpr int EMIT3_CELLS = EMIT3_CELLS_PER_THREAD;
-constexpr int EMIT3_ROWS = TILE_H * EMIT3_CELLS;  // cell rows per block
+constexpr int EMIT3_ROWS = E3_H * EMIT3_CELLS;  // cell rows per block
 constexpr int EMIT3_PEND = 4;
 
 constexpr size_t emit3_smem_bytes() {
-  return (size_t)EMIT3_PEND * (TILE_W * TILE_H) * 16                          // parked pairs
-         + (size_t)(TILE_W * TILE_H / 32) * 64 * sizeof(int)                  // warp queues
-         + (size_t)(TILE_W * 33 + EMIT3_ROWS * 9) * sizeof(double);           // prior tables
+  return (size_t)EMIT3_PEND * (E3_W * E3_H) * 16                          // parked pairs
+         + (size_t)(E3_W * E3_H / 32) * 64 * sizeof(int)                  // warp queues
+         + (size_t)(E3_W * 33 + EMIT3_ROWS * 9) * sizeof(double);           // prior tables
 }
 
-template <typename LabelT>
-__global__ void __launch_bounds__(TILE_W * TILE_H, EMIT3_MIN_BLOCKS)
+// v[i] for a run-time i out of 64 registers: a six-level select tree (63 selects) instead of a
+// trip to memory for the label of the first uncovered pixel
+__device__ __forceinline__ int pick64(const int (&v)[64], int i) {
+  int a[32], b[16], c[8], d[4];
+  const bool b0 = i & 1, b1 = i & 2, b2 = i & 4, b3 = i & 8, b4 = i & 16, b5 = i & 32;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = b0 ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) b[j] = b1 ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j] = b2 ? b[2 * j + 1] : b[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = b3 ? c[2 * j + 1] : c[2 * j];
+  const int e0 = b4 ? d[1] : d[0], e1 = b4 ? d[3] : d[2];
+  return b5 ? e1 : e0;
+}
+
+// 32 bytes of labels (one pixel row of a cell of 32-bit labels, half a row of 64-bit ones):
+// one 256-bit load where the label map is 32-byte aligned (sm_100 LDG.256: half the load
+// instructions and L1 tag look-ups of two 128-bit loads), else two 128-bit loads
+template <bool V8>
+__device__ __forceinline__ void ld_labels32(const void* p, int4& a, int4& b) {
+  if (V8) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z),
+                   "=r"(b.w)
+                 : "l"(p));
+  } else {
+    a = __ldg(reinterpret_cast<const int4*>(p));
+    b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  }
+}
+
+template <typename LabelT, bool V8>
+__global__ void __launch_bounds__(E3_W * E3_H, EMIT3_MIN_BLOCKS)
 emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw,
                  const int64_t* __restrict__ sp_off, S8Ws ws, int64_t spill_cap,
                  int64_t* nnz_flags, PriorTabs pt, const double* __restrict__ gy,
                  bool have_prior) {
-  constexpr int NT = TILE_W * TILE_H, NWARP = NT / 32;
+  constexpr int NT = E3_W * E3_H, NWARP = NT / 32;
   constexpr int PER_ROW = 8 * (int)sizeof(LabelT) / 16;  // 16-byte chunks per pixel row of a cell
   extern __shared__ int4 s_dyn[];
   int4 (*s_pend)[NT] = reinterpret_cast<int4 (*)[NT]>(s_dyn);  // (row, packed, prior lo, hi)
   int (*s_q)[64] = reinterpret_cast<int (*)[64]>(s_dyn + EMIT3_PEND * NT);
   double (*s_T)[33] = reinterpret_cast<double (*)[33]>(s_dyn + EMIT3_PEND * NT + NWARP * 64 / 4);
-  double* s_gy = reinterpret_cast<double*>(s_T + TILE_W);  // [EMIT3_ROWS * 8] = gy of the rows
+  double* s_gy = reinterpret_cast<double*>(s_T + E3_W);  // [EMIT3_ROWS * 8] = gy of the rows
   double* s_gy8 = s_gy + EMIT3_ROWS * 8;                   // [EMIT3_ROWS]
-  const int t = threadIdx.x, tx = t & (TILE_W - 1), ty = t / TILE_W;
+  const int t = threadIdx.x, tx = t & (E3_W - 1), ty = t / E3_W;
   const int lane = t & 31, wid = t >> 5;
   const int img = blockIdx.z;
-  const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * EMIT3_ROWS;
+  const int bx0 = blockIdx.x * E3_W, by0 = blockIdx.y * EMIT3_ROWS;
   const int cx = bx0 + tx;
   const bool in_x = cx < fw;
   const LabelT* limg = labels + (size_t)img * H * W;
   const LabelT* pcol = limg + (size_t)cx * 8;
   if (have_prior) {
     // all loads first, then the stores: one round trip instead of one per loop iteration
-    constexpr int NTAB = (TILE_W * 33 + NT - 1) / NT, NGY = EMIT3_ROWS * 8 / NT;
+    constexpr int NTAB = (E3_W * 33 + NT - 1) / NT, NGY = EMIT3_ROWS * 8 / NT;
     double tab[NTAB], g[NGY], g8 = 0.0;
 #pragma unroll
     for (int i = 0; i < NTAB; ++i) {
       const int e = t + i * NT, c = e / 33, k = e - c * 33, gc = bx0 + c;
       tab[i] = 0.0;
-      if (e < TILE_W * 33 && gc < fw) tab[i] = k < 32 ? pt.gxT[(size_t)gc * 32 + k] : pt.gx8[gc];
+      if (e < E3_W * 33 && gc < fw) tab[i] = k < 32 ? pt.gxT[(size_t)gc * 32 + k] : pt.gx8[gc];
     }
 #pragma unroll
     for (int i = 0; i < NGY; ++i) {
@@ -1262,7 +1303,7 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
 #pragma unroll
     for (int i = 0; i < NTAB; ++i) {
       const int e = t + i * NT;
-      if (e < TILE_W * 33) s_T[e / 33][e % 33] = tab[i];
+      if (e < E3_W * 33) s_T[e / 33][e % 33] = tab[i];
     }
 #pragma unroll
     for (int i = 0; i < NGY; ++i) s_gy[t + i * NT] = g[i];
@@ -1287,7 +1328,7 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
   // phase B: all label passes of one mixed cell (code = local cell row * 16 + local column)
   auto mixed_cell = [&](int code) {
     place_parked();
-    const int ly = code >> 4, lx = code & (TILE_W - 1);
+    const int ly = code / E3_W, lx = code % E3_W;
     const int cyy = by0 + ly, cxx = bx0 + lx;
     const int c = cyy * fw + cxx;
     const LabelT* p = limg + (size_t)cyy * 8 * W + (size_t)cxx * 8;
@@ -1295,16 +1336,21 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int h = 0; h < PER_ROW; ++h) {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + h);
-        const int k = r * PER_ROW + h;
-        if (sizeof(LabelT) == 4) {
-          v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-        } else {
-          const long long a = ((long long)q.y << 32) | (unsigned)q.x;
-          const long long b2 = ((long long)q.w << 32) | (unsigned)q.z;
-          v[2 * k] = (a >= 0 && a < n_sp) ? (int)a : -1;
-          v[2 * k + 1] = (b2 >= 0 && b2 < n_sp) ? (int)b2 : -1;
+      for (int h2 = 0; h2 < PER_ROW; h2 += 2) {
+        int4 qq[2];
+        ld_labels32<V8>(reinterpret_cast<const int4*>(p + (size_t)r * W) + h2, qq[0], qq[1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int4 q = qq[j];
+          const int k = r * PER_ROW + h2 + j;
+          if (sizeof(LabelT) == 4) {
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+          } else {
+            const long long a = ((long long)q.y << 32) | (unsigned)q.x;
+            const long long b2 = ((long long)q.w << 32) | (unsigned)q.z;
+            v[2 * k] = (a >= 0 && a < n_sp) ? (int)a : -1;
+            v[2 * k + 1] = (b2 >= 0 && b2 < n_sp) ? (int)b2 : -1;
+          }
         }
       }
     const double cell_prior = have_prior ? __dmul_rn(s_gy8[ly], s_T[lx][32]) : 0.0;
@@ -1326,10 +1372,14 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
       remaining &= ~m;
       int nextl = 0;
       if (remaining != 0ull) {
+#if EMIT3_PICK_TREE
+        nextl = pick64(v, __ffsll((long long)remaining) - 1);
+#else
         const int i = __ffsll((long long)remaining) - 1;
         const LabelT nextq = __ldg(p + (size_t)(i >> 3) * W + (i & 7));
         nextl = (sizeof(LabelT) == 4) ? (int)nextq
                                       : ((nextq >= 0 && nextq < (LabelT)n_sp) ? (int)nextq : -1);
+#endif
       }
       if ((unsigned)L < (unsigned)n_sp) {
         const int cnt = __popc(lo) + __popc(hi);
@@ -1384,9 +1434,9 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
   double upend_prior = 0.0;
 #pragma unroll 1
   for (int it = 0; it < EMIT3_CELLS; ++it) {
-    const int ly = it * TILE_H + ty;
+    const int ly = it * E3_H + ty;
     const int cy = by0 + ly;
-    if (by0 + it * TILE_H + 2 * wid >= fh) break;  // warp-uniform: both cell rows of the warp
+    if (by0 + it * E3_H + wid * 32 / E3_W >= fh) break;  // warp-uniform: first cell row of the warp
     const bool act = in_x && cy < fh;
     int v0 = 0;
     bool uniform = false, mixed = false;
@@ -1395,10 +1445,7 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
       if (sizeof(LabelT) == 4) {
         int4 q[16];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          q[2 * r] = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W));
-          q[2 * r + 1] = __ldg(reinterpret_cast<const int4*>(p + (size_t)r * W) + 1);
-        }
+        for (int r = 0; r < 8; ++r) ld_labels32<V8>(p + (size_t)r * W, q[2 * r], q[2 * r + 1]);
         v0 = q[0].x;
         unsigned diff = 0;
 #pragma unroll
@@ -1419,9 +1466,9 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
 #pragma unroll
           for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int h = 0; h < 4; ++h)
-              q[4 * r + h] =
-                  __ldg(reinterpret_cast<const int4*>(p + (size_t)(4 * half + r) * W) + h);
+            for (int h = 0; h < 4; h += 2)
+              ld_labels32<V8>(reinterpret_cast<const int4*>(p + (size_t)(4 * half + r) * W) + h,
+                              q[4 * r + h], q[4 * r + h + 1]);
           if (half == 0) { v0 = q[0].x; v0h = q[0].y; }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -1442,7 +1489,7 @@ emit_s8v3_kernel(const LabelT* __restrict__ labels, int H, int W, int fh, int fw
       upend = false;
     }
     const unsigned mb = __ballot_sync(0xffffffffu, mixed);
-    if (mixed) s_q[wid][qn + __popc(mb & ((1u << lane) - 1u))] = ly * TILE_W + tx;
+    if (mixed) s_q[wid][qn + __popc(mb & ((1u << lane) - 1u))] = ly * E3_W + tx;
     qn += __popc(mb);
     __syncwarp();
     if (qn >= 32) {
@@ -1891,22 +1938,23 @@ extern "C" int spalign_overlap_csr(const void* labels, int label_dtype, int n_im
             (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy != nullptr);
       }
     } else {
-      dim3 egrid((fw + TILE_W - 1) / TILE_W, (fh + EMIT3_ROWS - 1) / EMIT3_ROWS, n_img);
+      dim3 egrid((fw + E3_W - 1) / E3_W, (fh + EMIT3_ROWS - 1) / EMIT3_ROWS, n_img);
+      constexpr size_t smem = emit3_smem_bytes();
+      const bool v8 = reinterpret_cast<size_t>(labels) % 32 == 0 &&  // 256-bit label loads
+                      getenv("SPALIGN_K1_LD128") == nullptr;
+#define SPALIGN_EMIT3(LT, V8)                                                                  \
+  do {                                                                                         \
+    SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v3_kernel<LT, V8>,                                \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    emit_s8v3_kernel<LT, V8><<<egrid, NT, smem, stream>>>(                                     \
+        (const LT*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy, gy != nullptr); \
+  } while (0)
       if (label_dtype == SPALIGN_I32) {
-        constexpr size_t smem = emit3_smem_bytes();
-        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v3_kernel<int32_t>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emit_s8v3_kernel<int32_t><<<egrid, NT, smem, stream>>>(
-            (const int32_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy,
-            gy != nullptr);
+        if (v8) SPALIGN_EMIT3(int32_t, true); else SPALIGN_EMIT3(int32_t, false);
       } else {
-        constexpr size_t smem = emit3_smem_bytes();
-        SPALIGN_CUDA(cudaFuncSetAttribute(emit_s8v3_kernel<int64_t>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emit_s8v3_kernel<int64_t><<<egrid, NT, smem, stream>>>(
-            (const int64_t*)labels, H, W, fh, fw, sp_off, w8, nnz_cap, nnz_flags, pt, gy,
-            gy != nullptr);
+        if (v8) SPALIGN_EMIT3(int64_t, true); else SPALIGN_EMIT3(int64_t, false);
       }
+#undef SPALIGN_EMIT3
     }
     const int n_tiles = (int)((n_rows + SCAN_TILE - 1) / SCAN_TILE);
     scan_tile_sums_kernel<<<n_tiles, 256, 0, stream>>>(w8.cursor, n_rows, w8.tile_sum);
