@@ -70,6 +70,29 @@ def test_overlap_stride8_voronoi(ops, dtype):
     _check_overlap(ops, labs, 8, 16)
 
 
+@pytest.mark.parametrize('dtype', [torch.int32, torch.int64])
+def test_overlap_stride8_label_pointer_alignment(ops, dtype):
+    """emit v3 loads 32 bytes of labels at a time where the map is 32-byte aligned and 2 x 16
+    bytes otherwise: a label map that starts 16 bytes into an allocation gives the same matrix."""
+    labs = np.stack([synth.voronoi_labels(64, 128, 4, 8, image_index=20 + i) for i in range(3)])
+    n_sp = [int(l.max()) + 1 for l in labs]
+    aligned = torch.from_numpy(labs).to(dev()).to(dtype)
+    shift = 16 // aligned.element_size()
+    buf = torch.zeros(aligned.numel() + shift, dtype=dtype, device=dev())
+    shifted = buf[shift:].view(aligned.shape)
+    shifted.copy_(aligned)
+    assert aligned.data_ptr() % 32 == 0 and shifted.data_ptr() % 32 == 16
+    a = ops.overlap_csr(aligned, 8, 16, n_sp, prior=PRIOR)
+    b = ops.overlap_csr(shifted, 8, 16, n_sp, prior=PRIOR)
+    nnz = a.validate()
+    assert nnz == b.validate()
+    for name in ('indptr', 'area', 'sum_y', 'sum_x', 'sum_prior'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for name in ('indices', 'counts'):
+        assert torch.equal(getattr(a, name)[:nnz], getattr(b, name)[:nnz]), name
+    _check_overlap(ops, list(labs), 8, 16)
+
+
 @pytest.mark.parametrize('H,W,fh,fw,gy,gx', [(50, 70, 7, 9, 3, 4), (224, 224, 28, 28, 7, 7),
                                              (33, 47, 33, 47, 3, 3), (40, 40, 1, 1, 2, 2),
                                              (64, 128, 16, 32, 4, 8), (30, 50, 40, 60, 2, 3)])
