@@ -248,6 +248,21 @@ def run_batch_overlapped(labels: torch.Tensor, feat_cellmajor: torch.Tensor,
     return OverlappedOutput(cmap, mask, parts)
 
 
+def _raise_on_overlap_flags(words, index):
+    """The K1 condition words of sub-batch ``index`` (copied back with its result): the same
+    errors ``Overlap.validate()`` / ``PipelineOutput.check()`` raise.  On a capacity overflow K1
+    left an EMPTY matrix, so the maps handed back would be meaningless, not unsafe."""
+    nnz, flags, hw, _ = [int(v) for v in words.tolist()]
+    if flags & _lib.F_NNZ_OVERFLOW:
+        raise OverflowError('sub-batch %d: overlap CSR capacity exceeded (nnz=%d, per-image high '
+                            'water %d); pass a larger nnz_cap_per_image' % (index, nnz, hw))
+    if flags & _lib.F_LABEL_RANGE:
+        raise ValueError('sub-batch %d: label outside [0, n_sp)' % index)
+    if flags & _lib.F_EMPTY_ROW:
+        raise ValueError('sub-batch %d: label ids are not contiguous 0..S-1 (rows without pixels)'
+                         % index)
+
+
 class HostPipeline:
     """End-to-end path for inputs that live in HOST memory (pinned): label maps and cell-major
     feature maps go host -> device on a copy stream while the previous sub-batch is being
@@ -274,6 +289,7 @@ class HostPipeline:
                      for _ in range(2)]
         self.out_c = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.out_m = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.flags = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.copy = torch.cuda.Stream(device=d)
         self.comp = torch.cuda.Stream(device=d)
         self.h2d_bytes = 0
@@ -319,12 +335,14 @@ class HostPipeline:
             if pending is not None:      # hand the previous result to the caller
                 pi, ps, pb, pev = pending
                 pev.synchronize()
+                _raise_on_overlap_flags(self.flags[ps], pi)
                 if on_result is not None:
                     on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(ev_c)
                 self.out_c[s][:b].copy_(out.cluster_map, non_blocking=True)
                 self.out_m[s][:b].copy_(out.road_mask, non_blocking=True)
+                self.flags[s].copy_(out.overlap.nnz_flags, non_blocking=True)
                 ev_d = torch.cuda.Event()
                 ev_d.record(self.copy)
             out.cluster_map.record_stream(self.copy)
@@ -334,6 +352,7 @@ class HostPipeline:
             up = nxt
         pi, ps, pb, pev = pending
         pev.synchronize()
+        _raise_on_overlap_flags(self.flags[ps], pi)
         if on_result is not None:
             on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
 
@@ -391,6 +410,7 @@ class ImagePipeline:
         self.lab = [torch.empty((sub_batch, H, W), dtype=label_dtype, device=d) for _ in range(2)]
         self.out_c = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.out_m = [torch.empty((sub_batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.flags = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.copy = torch.cuda.Stream(device=d)
         self.comp = torch.cuda.Stream(device=d)
         self.mean = torch.tensor(self.MEAN, device=d).view(1, 3, 1, 1) * 255.0
@@ -463,12 +483,14 @@ class ImagePipeline:
             if pending is not None:
                 pi, ps, pb, pev = pending
                 pev.synchronize()
+                _raise_on_overlap_flags(self.flags[ps], pi)
                 if on_result is not None:
                     on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(ev_c)
                 self.out_c[s][:b].copy_(out.cluster_map, non_blocking=True)
                 self.out_m[s][:b].copy_(out.road_mask, non_blocking=True)
+                self.flags[s].copy_(out.overlap.nnz_flags, non_blocking=True)
                 ev_d = torch.cuda.Event()
                 ev_d.record(self.copy)
             out.cluster_map.record_stream(self.copy)
@@ -478,5 +500,6 @@ class ImagePipeline:
             up = nxt
         pi, ps, pb, pev = pending
         pev.synchronize()
+        _raise_on_overlap_flags(self.flags[ps], pi)
         if on_result is not None:
             on_result(pi, self.out_c[ps][:pb], self.out_m[ps][:pb])

@@ -184,6 +184,32 @@ def test_host_pipeline_streams_batches_and_matches_device_path():
         assert torch.equal(ref.road_mask.cpu(), got[i][1])
 
 
+def test_host_pipeline_reports_label_problems_with_the_result():
+    """The K1 condition words travel back with every sub-batch: a label outside [0, n_sp) or ids
+    with gaps raise at the point where the result would have been handed over."""
+    from superpixel_align_b200 import pipeline
+    H, W, fh, fw, C = 128, 256, 16, 32, 32
+    labs = np.stack([synth.voronoi_labels(H, W, 6, 10, image_index=i) for i in range(4)])
+    feats = np.stack([synth.smooth_features(C, fh, fw, seed=i).reshape(C, -1).T for i in range(4)])
+    h_feat = torch.from_numpy(np.ascontiguousarray(feats)).pin_memory()
+    bad = labs.copy()
+    bad[3, 5, 7] = 1000                       # out of range in the second sub-batch
+    h_bad = torch.from_numpy(bad).pin_memory()
+    hp = pipeline.HostPipeline(H, W, fh, fw, C, sub_batch=2, k=4)
+    seen = []
+    np.random.seed(7)
+    with pytest.raises(ValueError, match='sub-batch 1'):
+        hp.process([(h_bad[0:2], h_feat[0:2], [60, 60]), (h_bad[2:4], h_feat[2:4], [60, 60])],
+                   lambda i, c, m: seen.append(i))
+    assert seen == [0]
+    gap = labs.copy()
+    gap[gap == 59] = 60                       # id 59 has no pixels: 0/0 weights downstream
+    h_gap = torch.from_numpy(gap).pin_memory()
+    np.random.seed(7)
+    with pytest.raises(ValueError, match='not contiguous'):
+        hp.process([(h_gap[0:2], h_feat[0:2], [61, 61])], None)
+
+
 def test_run_batch_overlapped_on_side_streams_equals_one_batch():
     from superpixel_align_b200 import pipeline
     d = torch.device('cuda', 0)
