@@ -324,6 +324,24 @@ int spalign_slic(const float* images, int n_img, int H, int W, int n_segments, d
                  int32_t* labels, int32_t* n_labels, void* workspace, size_t ws_bytes,
                  spalign_stream_t stream);
 
+/* ---- f3, second branch: Felzenszwalb-Huttenlocher superpixels ---------------------------------
+ * Replaces batch_superpixel() batch_spalign_kmeans.py:301-307, the reference's DEFAULT
+ * --superpixel_method (skimage.segmentation.felzenszwalb(img.transpose(1, 2, 0) / 255.,
+ * scale=300, sigma=0.8, min_size=20), one image at a time on the CPU).  Contract: the algorithm of
+ * scikit-image 0.13 as restated in oracle/spalign_oracle.py:felzenszwalb -- Gaussian smoothing
+ * (scipy.ndimage.gaussian_filter, reflect), 8-connectivity edge costs, edges in ascending cost
+ * (equal costs in edge order: the one point skimage leaves to np.argsort), greedy merges while
+ * cost < min(Int(a) + k/|a|, Int(b) + k/|b|) with k = scale / 255, then the min_size pass, labels
+ * numbered by ascending union-find root.  Float64 in the oracle's operation order: bit-identical
+ * labels.  PARITY UNPINNED by the reference (scikit-image is not in its tree).
+ *   images  [n_img, 3, H, W] float32 (CHW; values in 0..1)
+ *   labels  [n_img, H, W] int32 out, ids 0..S-1; n_labels[n_img] int32 out
+ * The merge pass is sequential by definition; images are processed side by side (one CTA each). */
+size_t spalign_felzenszwalb_workspace_bytes(int n_img, int H, int W);
+int spalign_felzenszwalb(const float* images, int n_img, int H, int W, double scale, double sigma,
+                         int min_size, int32_t* labels, int32_t* n_labels, void* workspace,
+                         size_t ws_bytes, spalign_stream_t stream);
+
 /* ---- K4: paint-back -------------------------------------------------------------------
  * Replaces the double loop of weighted_kmeans() batch_spalign_kmeans.py:193-199 and the
  * `== 0` road mask (:207): cluster_map[p] = table[sp_off[img] + label[p]] (0 when the label

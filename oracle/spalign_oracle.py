@@ -687,3 +687,109 @@ def replay_reference_anchors(label, n_select=10):
         anchors[i, :len(sel)] = np.asarray(sel)
         n_valid[i] = len(sel)
     return anchors, n_valid
+
+
+# ---------------------------------------------------------------------------------------
+# Felzenszwalb-Huttenlocher graph segmentation as scikit-image 0.13 runs it
+# (skimage/segmentation/_felzenszwalb_cy.pyx; called at batch_spalign_kmeans.py:303-307 with
+# img / 255., scale=300, sigma=0.8, min_size=20).  scikit-image is not in the reference tree:
+# PARITY UNPINNED; this restatement is the contract of spalign_felzenszwalb.  One choice is
+# pinned where skimage leaves it open: edges of equal cost keep their index order (stable sort;
+# skimage uses np.argsort's default, whose tie order is unspecified).
+
+def felz_weights(sigma, truncate=4.0):
+    """scipy.ndimage 1-D Gaussian (order 0): (radius, weights[0..radius] by distance)."""
+    lw = int(truncate * float(sigma) + 0.5)
+    sd = float(sigma) * float(sigma)
+    w = [1.0]
+    tot = 1.0
+    for ii in range(1, lw + 1):
+        tmp = np.exp(-0.5 * float(ii * ii) / sd)
+        w.append(float(tmp))
+        tot += 2.0 * float(tmp)
+    return lw, np.asarray(w, dtype=np.float64) / tot
+
+
+def _felz_reflect(i, n):
+    while i < 0 or i >= n:
+        i = -i - 1 if i < 0 else 2 * n - 1 - i
+    return i
+
+
+def felz_blur(img, sigma):
+    """gaussian_filter(img [H, W, C] float64, sigma=[sigma, sigma, 0]), mode 'reflect': axis 0
+    then axis 1, each output = x*w0 + sum over distance d = radius..1 of (x[-d] + x[+d])*w[d]
+    (the symmetric branch of scipy's correlate1d, plain multiplies and adds)."""
+    lw, w = felz_weights(sigma)
+    out = np.asarray(img, dtype=np.float64)
+    for axis in (0, 1):
+        n = out.shape[axis]
+        x = np.moveaxis(out, axis, 0)
+        idx = lambda off: np.asarray([_felz_reflect(i + off, n) for i in range(n)])
+        acc = x * w[0]
+        for d in range(lw, 0, -1):
+            acc = acc + (x[idx(-d)] + x[idx(d)]) * w[d]
+        out = np.moveaxis(acc, 0, axis)
+    return out
+
+
+def felz_edges(H, W):
+    """Edge endpoints in skimage's order: right, down, down-right, up-right."""
+    seg = np.arange(H * W).reshape(H, W)
+    right = np.c_[seg[:, 1:].ravel(), seg[:, :W - 1].ravel()]
+    down = np.c_[seg[1:, :].ravel(), seg[:H - 1, :].ravel()]
+    dright = np.c_[seg[1:, 1:].ravel(), seg[:H - 1, :W - 1].ravel()]
+    uright = np.c_[seg[:H - 1, 1:].ravel(), seg[1:, :W - 1].ravel()]
+    return np.vstack([right, down, dright, uright])
+
+
+def felz_costs(sm):
+    H, W = sm.shape[:2]
+
+    def cost(a, b):
+        d = a - b
+        return np.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+    return np.hstack([cost(sm[:, 1:], sm[:, :W - 1]).ravel(), cost(sm[1:], sm[:H - 1]).ravel(),
+                      cost(sm[1:, 1:], sm[:H - 1, :W - 1]).ravel(),
+                      cost(sm[1:, :W - 1], sm[:H - 1, 1:]).ravel()])
+
+
+def felzenszwalb(img_chw, scale=300.0, sigma=0.8, min_size=20):
+    """[3, H, W] float32 image with values in 0..1 -> int32 [H, W] labels 0..S-1, numbered in the
+    order of np.unique over the union-find roots (a root is the smallest pixel index of its set)."""
+    img = np.asarray(img_chw, dtype=np.float32).transpose(1, 2, 0).astype(np.float64)
+    H, W, _ = img.shape
+    scale = float(scale) / 255.0
+    sm = felz_blur(img, sigma) if sigma > 0 else img
+    costs = felz_costs(sm)
+    edges = felz_edges(H, W)
+    order = np.argsort(costs, kind='stable')
+    parent = np.arange(H * W)
+    size = np.ones(H * W, dtype=np.int64)
+    cint = np.zeros(H * W)
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+    for e in order:
+        a, b = find(edges[e, 0]), find(edges[e, 1])
+        if a == b:
+            continue
+        c = costs[e]
+        if c < min(cint[a] + scale / size[a], cint[b] + scale / size[b]):
+            r, o = (a, b) if a < b else (b, a)
+            parent[o] = r
+            size[r] = size[a] + size[b]
+            cint[r] = c
+    for e in order:
+        a, b = find(edges[e, 0]), find(edges[e, 1])
+        if a == b:
+            continue
+        if size[a] < min_size or size[b] < min_size:
+            r, o = (a, b) if a < b else (b, a)
+            parent[o] = r
+            size[r] = size[a] + size[b]
+    roots = np.asarray([find(i) for i in range(H * W)])
+    return np.unique(roots, return_inverse=True)[1].reshape(H, W).astype(np.int32)

@@ -61,6 +61,8 @@ SIGNATURES = {
     'spalign_slic_segments': (_i, [_i, _i, _i]),
     'spalign_slic_workspace_bytes': (_z, [_i, _i, _i, _i]),
     'spalign_slic': (_i, [_p, _i, _i, _i, _i, _d, _i, _i, _i, _d, _p, _p, _p, _z, _p]),
+    'spalign_felzenszwalb_workspace_bytes': (_z, [_i, _i, _i]),
+    'spalign_felzenszwalb': (_i, [_p, _i, _i, _i, _d, _d, _i, _p, _p, _p, _z, _p]),
     'spalign_paint': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p]),
     'spalign_refine': (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p]),
     'spalign_resize_nearest_u8': (_i, [_p, _i, _i, _i, _p, _i, _i, _p]),

@@ -347,25 +347,31 @@ def superpixel_align(img, feature_map, superpixels, n_select=10, n_neighbor=4, a
 
 
 def batch_superpixel(args, imgs):
-    """Label maps of a batch -- batch_spalign_kmeans.py:299-313 for ``--superpixel_method slic``
-    (``slic(img.transpose(1, 2, 0), args.n_slic_segments)``), on the device.
+    """Label maps of a batch -- batch_spalign_kmeans.py:299-313, on the device: the reference's
+    default ``--superpixel_method felzenszwalb`` (``felzenszwalb(img.transpose(1, 2, 0) / 255.,
+    scale=args.felzenszwalb_scale, sigma=args.felzenszwalb_sigma,
+    min_size=args.felzenszwalb_min_size)``) and ``slic`` (``slic(img.transpose(1, 2, 0),
+    args.n_slic_segments)``).
 
     imgs [n, 3, H, W] float (0..255 as the reference holds them); returns int64 NumPy [n, H, W] for
     NumPy input (what skimage yields), int32 CUDA for torch input.  The images are divided by 255
-    first: skimage 0.13 refuses float images outside [-1, 1] (``img_as_float``), so the
-    reference's slic branch -- which none of its shipped drivers uses -- only runs on scaled
-    input; its felzenszwalb branch (:303-307) scales by ``/ 255.`` itself.  Parity with skimage
-    is unpinned (not in the tree): the contract is oracle/spalign_oracle.py:slic.
-    felzenszwalb is not built (label maps are an input of the hot path)."""
-    method = getattr(args, 'superpixel_method', 'slic')
-    if method != 'slic':
-        raise NotImplementedError("superpixel_method %r: only 'slic' runs on the device; pass label "
-                                  "maps computed elsewhere to the batch_* functions" % method)
+    in both branches: the reference does so itself for felzenszwalb (:304); skimage 0.13 refuses
+    float images outside [-1, 1] (``img_as_float``), so its slic branch -- which none of its
+    shipped drivers uses -- only runs on scaled input.  Parity with skimage is unpinned (not in
+    the tree): the contracts are oracle/spalign_oracle.py:felzenszwalb and :slic."""
+    method = getattr(args, 'superpixel_method', 'felzenszwalb')
+    if method not in ('felzenszwalb', 'slic'):
+        raise ValueError('superpixel_method %r: felzenszwalb or slic' % (method,))
     iu = _unwrap(imgs)
     as_numpy = not isinstance(iu, torch.Tensor)
     dev = _device(args) if as_numpy else iu.device
     x = _to_dev(iu, dev, torch.float32) / 255.0
-    labels, _ = ops.slic(x, int(getattr(args, 'n_slic_segments', 100)))
+    if method == 'felzenszwalb':
+        labels, _ = ops.felzenszwalb(x, float(getattr(args, 'felzenszwalb_scale', 300.0)),
+                                     float(getattr(args, 'felzenszwalb_sigma', 0.8)),
+                                     int(getattr(args, 'felzenszwalb_min_size', 20)))
+    else:
+        labels, _ = ops.slic(x, int(getattr(args, 'n_slic_segments', 100)))
     return labels.cpu().numpy().astype(np.int64) if as_numpy else labels
 
 

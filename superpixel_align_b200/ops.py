@@ -728,6 +728,35 @@ def kmeans_init_device(w: torch.Tensor, group_off: torch.Tensor, shuffled: torch
 
 
 # --------------------------------------------------------------------------------------
+def felzenszwalb(images: torch.Tensor, scale: float = 300.0, sigma: float = 0.8,
+                 min_size: int = 20, chunk: int = 64):
+    """f3: Felzenszwalb-Huttenlocher label maps on the device (the reference's default
+    superpixel method).  images [n, 3, H, W] float32 CUDA (values in 0..1) -> (labels int32
+    [n, H, W] with ids 0..S-1, n_labels int32 [n]).  Contract and oracle:
+    oracle/spalign_oracle.py:felzenszwalb (parity unpinned: scikit-image is not in the reference
+    tree).  ``chunk`` images share one workspace (their merge passes run side by side)."""
+    global LAUNCHES
+    _require_cuda(images)
+    assert images.dim() == 4 and images.shape[1] == 3
+    images = images.float().contiguous()
+    n, _, H, W = images.shape
+    dev = images.device
+    lib = _lib.load()
+    labels = torch.empty((n, H, W), dtype=torch.int32, device=dev)
+    n_labels = torch.empty(n, dtype=torch.int32, device=dev)
+    chunk = max(1, min(chunk, n))
+    ws_bytes = lib.spalign_felzenszwalb_workspace_bytes(chunk, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        check(lib.spalign_felzenszwalb(_ptr(images[i:]), m, H, W, float(scale), float(sigma),
+                                       int(min_size), _ptr(labels[i:]), _ptr(n_labels[i:]),
+                                       _ptr(ws), ws_bytes, _stream()), 'felzenszwalb')
+        LAUNCHES += 6 + 3 * m   # blur x2, costs, merge, relabel; radix sort passes per image
+    return labels, n_labels
+
+
+# --------------------------------------------------------------------------------------
 def slic(images: torch.Tensor, n_segments: int = 100, compactness: float = 10.0, max_iter: int = 10,
          convert2lab: bool = True, enforce_connectivity: bool = True, min_size_factor: float = 0.5,
          chunk: int = 16):

@@ -94,5 +94,47 @@ def test_batch_superpixel_dropin_feeds_the_pipeline():
     np.random.seed(1)
     cres, road = bsk.batch_weighted_kmeans(args, sp, f, w, n_per)
     assert cres.shape == sp.shape and road.dtype == bool
-    with pytest.raises(NotImplementedError):
-        bsk.batch_superpixel(types.SimpleNamespace(superpixel_method='felzenszwalb'), imgs)
+    with pytest.raises(ValueError):
+        bsk.batch_superpixel(types.SimpleNamespace(superpixel_method='watershed'), imgs)
+
+
+# ------------------------------------------------------------------ felzenszwalb (f3, default)
+@pytest.mark.parametrize('H,W,scale,sigma,min_size', [(40, 56, 8.0, 0.8, 20), (33, 47, 3.0, 0.8, 5),
+                                                      (24, 64, 20.0, 1.5, 10), (32, 32, 5.0, 0.0, 4),
+                                                      (16, 16, 300.0, 0.8, 20)])
+def test_felzenszwalb_labels_equal_the_oracle(H, W, scale, sigma, min_size):
+    """Bit-identical label maps against the NumPy restatement of skimage 0.13's algorithm
+    (float64 in the same operation order; equal costs in edge order), several images side by
+    side; ids are contiguous and every id is present."""
+    from superpixel_align_b200 import ops
+    imgs = np.stack([_image(H, W, s) for s in (1, 2, 3)])
+    imgs[2, :, : H // 2] = imgs[2, :, :1, :1]            # a flat region: many zero-cost ties
+    lab, n_lab = ops.felzenszwalb(torch.from_numpy(imgs).to(dev()), scale, sigma, min_size)
+    lab, n_lab = lab.cpu().numpy(), n_lab.cpu().numpy()
+    for i in range(3):
+        ref = so.felzenszwalb(imgs[i], scale, sigma, min_size)
+        assert np.array_equal(lab[i], ref), (i, int(ref.max()) + 1, int(n_lab[i]))
+        assert n_lab[i] == ref.max() + 1 and np.array_equal(np.unique(lab[i]), np.arange(n_lab[i]))
+
+
+def test_felzenszwalb_larger_than_shared_memory_and_dropin_default():
+    """An image whose union-find does not fit shared memory takes the global-memory path (same
+    labels as the in-shared-memory path on the part both can run); the drop-in's default method
+    is the reference's (felzenszwalb) and its label maps feed K1."""
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk, ops
+    H, W = 64, 96
+    imgs = np.stack([_image(H, W, s) for s in (5, 6)]) * 255.0
+    args = types.SimpleNamespace(gpu=0, felzenszwalb_scale=6.0, felzenszwalb_sigma=0.8,
+                                 felzenszwalb_min_size=12)
+    sp = bsk.batch_superpixel(args, imgs)                 # no superpixel_method: the default
+    assert sp.shape == (2, H, W) and sp.dtype == np.int64
+    for i in range(2):
+        assert np.array_equal(sp[i], so.felzenszwalb(imgs[i] / np.float32(255.0), 6.0, 0.8, 12))
+    n_sp = [int(s.max()) + 1 for s in sp]
+    ov = ops.overlap_csr(torch.from_numpy(sp).to(dev()), H // 8, W // 8, n_sp)
+    assert ov.validate() > 0 and not ov.has_empty_rows
+    big = torch.from_numpy(np.stack([_image(240, 320, 9)])).to(dev())   # 76 800 px > 51 200
+    lab, n_lab = ops.felzenszwalb(big, 40.0, 0.8, 20)
+    lab = lab.cpu().numpy()[0]
+    assert int(n_lab[0]) == lab.max() + 1 and np.array_equal(np.unique(lab), np.arange(lab.max() + 1))
+    assert np.bincount(lab.ravel()).min() >= 20           # the min_size pass

@@ -282,3 +282,26 @@ def test_anchor_pooling_matches_reference_golden(golden_dir):
         np.testing.assert_allclose(want[:, C + 1], sx / area, rtol=1e-14)
         # with ties the restatement may pick other (equidistant) corner cells: bounded effect
         assert np.abs(got - want[:, :C]).max() < 0.5 * np.abs(want[:, :C]).max()
+
+
+def test_felzenszwalb_oracle_contract():
+    """The restatement of skimage 0.13's felzenszwalb: smoothing equals scipy's gaussian_filter
+    to rounding, labels are contiguous, every segment reaches min_size, a constant image is one
+    segment, and a larger scale merges more."""
+    from scipy import ndimage
+    rs = np.random.RandomState(3)
+    img = ndimage.uniform_filter(rs.rand(3, 36, 52), size=(1, 5, 5)).astype(np.float32)
+    hwc = img.transpose(1, 2, 0).astype(np.float64)
+    assert np.abs(so.felz_blur(hwc, 0.8) - ndimage.gaussian_filter(hwc, sigma=[0.8, 0.8, 0])).max() < 1e-15
+    lab = so.felzenszwalb(img, scale=4.0, sigma=0.8, min_size=9)
+    n = int(lab.max()) + 1
+    assert n > 3 and np.array_equal(np.unique(lab), np.arange(n))
+    assert np.bincount(lab.ravel()).min() >= 9
+    assert so.felzenszwalb(img, scale=40.0, sigma=0.8, min_size=9).max() + 1 < n
+    assert so.felzenszwalb(np.full((3, 12, 12), 0.5, np.float32), 1.0, 0.8, 4).max() == 0
+    # edges: skimage's order and endpoints (right, down, down-right, up-right)
+    e = so.felz_edges(3, 4)
+    assert len(e) == 3 * 3 + 2 * 4 + 2 * 2 * 3
+    assert e[0].tolist() == [1, 0] and e[9].tolist() == [4, 0] and e[17].tolist() == [5, 0] \
+        and e[23].tolist() == [1, 4]
+
