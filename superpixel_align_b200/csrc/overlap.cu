@@ -563,7 +563,6 @@ __global__ void __launch_bounds__(256)
 rowsort_warp_kernel(OverlapWs ws, int* indptr, int64_t R, int* indices,
                     int* counts, int* area, double* sum_prior, double* wvals,
                     const int64_t* __restrict__ nnz_flags, int ncell_hint) {
-  __shared__ unsigned s_keys[8][64];
   const int64_t r = (int64_t)blockIdx.x * 8 + warp_id();
   if (r >= R) return;
   const int lane = lane_id();
@@ -911,8 +910,9 @@ struct PriorTabs {
   const double* gx8;  // [fw]
   const double* gy8;  // [fh]
 };
-__device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx, int packed,
-                                             unsigned lo, unsigned hi) {  // (K1_PRIOR_IN_EMIT 0)
+[[maybe_unused]] __device__ __forceinline__ double pair_prior(const PriorTabs& pt, int cyy, int cxx,
+                                                              int packed, unsigned lo,
+                                                              unsigned hi) {  // (K1_PRIOR_IN_EMIT 0)
   if (packed_cnt(packed) == 64) return __dmul_rn(__ldg(pt.gy8 + cyy), __ldg(pt.gx8 + cxx));
   const double* T = pt.gxT + (size_t)cxx * 32;
   const double* g = pt.gyT + cyy;
