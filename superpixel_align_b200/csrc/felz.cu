@@ -13,8 +13,8 @@
 //   merge     the greedy pass over the sorted edges is sequential by definition (every decision
 //             depends on the component sizes all earlier merges left): one warp per image walks
 //             the edges -- 32 at a time are fetched and decoded by the lanes, lane 0 runs the
-//             union-find (parents in shared memory when the image fits: 224 x 224 does) -- and
-//             images run side by side, one CTA each.  Then the min_size pass, same order.
+//             union-find (parents and set sizes in shared memory when the image fits: 224 x 224
+//             does) -- and images run side by side, one CTA each.  Then the min_size pass.
 //   relabel   roots -> 0..S-1 in ascending root order (np.unique), block-wide scan
 #include <cub/device/device_radix_sort.cuh>
 
@@ -110,10 +110,13 @@ felz_cost_kernel(const double* __restrict__ sm, FelzGeom g, unsigned long long* 
   vals[(size_t)img * g.E + e] = (unsigned)e;
 }
 
+// union-find in ONE int per pixel: parent[i] >= 0 is the parent, parent[i] < 0 marks a root and
+// holds minus the size of its set (so the sizes live next to the parents, in shared memory)
 __device__ __forceinline__ int felz_find(int* parent, int i) {
   int p = parent[i];
-  while (p != i) {
+  while (p >= 0) {
     const int gp = parent[p];
+    if (gp < 0) return p;
     parent[i] = gp;  // path halving: never changes a root
     i = gp;
     p = parent[i];
@@ -124,17 +127,15 @@ __device__ __forceinline__ int felz_find(int* parent, int i) {
 // greedy merge + min_size pass of one image per CTA (one warp)
 __global__ void __launch_bounds__(32)
 felz_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ order,
-                  FelzGeom g, double scale, int min_size, int* parent_g, int* size_g, double* cint_g,
+                  FelzGeom g, double scale, int min_size, int* parent_g, double* cint_g,
                   int use_smem) {
   extern __shared__ int s_parent[];
   const int img = blockIdx.x, lane = threadIdx.x;
   const int n = g.H * g.W;
   int* parent = use_smem ? s_parent : parent_g + (size_t)img * n;
-  int* size = size_g + (size_t)img * n;
   double* cint = cint_g + (size_t)img * n;
   for (int i = lane; i < n; i += 32) {
-    parent[i] = i;
-    size[i] = 1;
+    parent[i] = -1;
     cint[i] = 0.0;
   }
   __syncwarp();
@@ -155,7 +156,7 @@ felz_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
         if (lane == 0) {
           const int ra = felz_find(parent, ea), rb = felz_find(parent, eb);
           if (ra != rb) {
-            const int sa = size[ra], sb = size[rb];
+            const int sa = -parent[ra], sb = -parent[rb];
             bool join;
             if (pass == 0) {
               const double ia = __dadd_rn(cint[ra], __ddiv_rn(scale, (double)sa));
@@ -167,7 +168,7 @@ felz_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned* _
             if (join) {
               const int r = min(ra, rb), o = max(ra, rb);
               parent[o] = r;
-              size[r] = sa + sb;
+              parent[r] = -(sa + sb);
               if (pass == 0) cint[r] = ec;
             }
           }
@@ -194,7 +195,7 @@ felz_relabel_kernel(int* parent_g, int n, int* rank_scratch, int32_t* labels, in
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += 1024) {
     const int i = i0 + t;
-    const int flag = (i < n && parent[i] == i) ? 1 : 0;
+    const int flag = (i < n && parent[i] < 0) ? 1 : 0;
     int incl = flag;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -222,7 +223,7 @@ felz_relabel_kernel(int* parent_g, int n, int* rank_scratch, int32_t* labels, in
   if (t == 0) n_labels[img] = s_base;
   for (int i = t; i < n; i += 1024) {
     int r = i;
-    while (parent[r] != r) r = parent[r];
+    while (parent[r] >= 0) r = parent[r];
     labels[(size_t)img * n + i] = rank[r];
   }
 }
@@ -234,8 +235,7 @@ struct FelzWs {
   unsigned long long* keys_alt;
   unsigned* vals;
   unsigned* vals_alt;
-  int* parent;       // [n_img][H*W]
-  int* size;
+  int* parent;       // [n_img][H*W] parent, or minus the set size at a root
   double* cint;      // (reused as rank scratch by the relabel pass)
   void* sort_tmp;
   size_t sort_tmp_bytes;
@@ -253,7 +253,6 @@ size_t felz_carve(FelzWs& ws, void* base, int n_img, int H, int W) {
   ws.vals = c.take<unsigned>((size_t)n_img * g.E);
   ws.vals_alt = c.take<unsigned>((size_t)n_img * g.E);
   ws.parent = c.take<int>((size_t)n_img * hw);
-  ws.size = c.take<int>((size_t)n_img * hw);
   ws.cint = c.take<double>((size_t)n_img * hw);
   ws.sort_tmp = c.take<char>(FELZ_SORT_TMP);
   ws.sort_tmp_bytes = FELZ_SORT_TMP;
@@ -347,7 +346,7 @@ extern "C" int spalign_felzenszwalb(const float* images, int n_img, int H, int W
     SPALIGN_CUDA(cudaFuncSetAttribute(felz_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)par_bytes));
   felz_merge_kernel<<<n_img, 32, use_smem ? par_bytes : 0, stream>>>(
-      skeys, svals, g, scale / 255.0, min_size, ws.parent, ws.size, ws.cint, use_smem);
+      skeys, svals, g, scale / 255.0, min_size, ws.parent, ws.cint, use_smem);
   felz_relabel_kernel<<<n_img, 1024, 0, stream>>>(ws.parent, H * W, reinterpret_cast<int*>(ws.cint),
                                                   labels, n_labels);
   return check_launch("felzenszwalb");
