@@ -7,12 +7,13 @@ import numpy as np
 import torch
 
 from . import ops
-from .batch_spalign_kmeans import _batch_state, _device, _to_dev, _unwrap
+from .batch_spalign_kmeans import (_batch_state, _device, _to_dev, _unwrap,
+                                   batch_superpixel)  # superpixel_overlaps.py:292-306, same function
 from .direct_clustering import (batch_weighted_kmeans, cluster_cells, create_prior, kmeans,
                                 weighted_average)
 
 __all__ = ['create_prior', 'kmeans', 'weighted_average', 'batch_weighted_kmeans',
-           'refine_road_masks', 'estimate_road_mask']
+           'batch_superpixel', 'refine_road_masks', 'estimate_road_mask']
 
 
 def refine_road_masks(superpixels, road_masks, overlap_threshold=0.01):
