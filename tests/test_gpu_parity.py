@@ -93,6 +93,38 @@ def test_overlap_stride8_label_pointer_alignment(ops, dtype):
     _check_overlap(ops, list(labs), 8, 16)
 
 
+@pytest.mark.parametrize('seed', range(12))
+def test_overlap_stride8_randomised_maps(ops, seed):
+    """emit v3 on random stride-8 geometries and label patterns (feature widths that are not a
+    multiple of the 32-cell tile, one-cell-high maps, noise with up to 64 labels per cell, stripes
+    one pixel wide, blocks aligned and misaligned with the cells, both label dtypes): bit-exact
+    CSR, areas, centroid sums; prior to 1e-12."""
+    rs = np.random.RandomState(1000 + seed)
+    fh, fw = int(rs.randint(1, 20)), int(rs.randint(1, 70))
+    H, W = 8 * fh, 8 * fw
+    kind = seed % 4
+    labs = []
+    for i in range(int(rs.randint(1, 4))):
+        if kind == 0:                                   # noise: many labels per cell
+            S = int(rs.randint(2, 200))
+            lab = rs.randint(0, S, size=(H, W))
+        elif kind == 1:                                 # stripes of random width
+            wd = int(rs.randint(1, 12))
+            lab = (np.arange(W)[None, :] // wd + np.arange(H)[:, None] // int(rs.randint(1, 12))
+                   * ((W + wd - 1) // wd))
+        elif kind == 2:                                 # blocks shifted against the cell grid
+            b, sy, sx = int(rs.randint(3, 30)), int(rs.randint(0, 8)), int(rs.randint(0, 8))
+            lab = ((np.arange(H)[:, None] + sy) // b) * ((W + 8 + b - 1) // b) + \
+                (np.arange(W)[None, :] + sx) // b
+        else:                                           # a few big blobs + sprinkled pixels
+            lab = (np.arange(H)[:, None] * 3 // max(H, 1)) * 3 + np.arange(W)[None, :] * 3 // max(W, 1)
+            m = rs.rand(H, W) < 0.02
+            lab = np.where(m, rs.randint(9, 40, size=(H, W)), lab)
+        u, inv = np.unique(lab, return_inverse=True)
+        labs.append(inv.reshape(H, W).astype(np.int64 if seed % 2 else np.int32))
+    _check_overlap(ops, labs, fh, fw)
+
+
 @pytest.mark.parametrize('H,W,fh,fw,gy,gx', [(50, 70, 7, 9, 3, 4), (224, 224, 28, 28, 7, 7),
                                              (33, 47, 33, 47, 3, 3), (40, 40, 1, 1, 2, 2),
                                              (64, 128, 16, 32, 4, 8), (30, 50, 40, 60, 2, 3)])
