@@ -210,6 +210,24 @@ def test_host_pipeline_reports_label_problems_with_the_result():
         hp.process([(h_gap[0:2], h_feat[0:2], [61, 61])], None)
 
 
+def test_staged_transfers_move_every_byte():
+    """The pinned-ring transfers of the NumPy drop-in (chunks of 32 MB, ragged tail, ring reuse):
+    identical bytes both ways, for the dtypes the drop-in moves."""
+    from superpixel_align_b200 import batch_spalign_kmeans as bsk
+    d = torch.device('cuda', 0)
+    rs = np.random.RandomState(0)
+    for dtype, n in ((np.float32, (5 * bsk._STAGE_CHUNK + 12345) // 4), (np.int64, (bsk._STAGE_CHUNK * 6) // 8 + 7),
+                     (np.uint8, bsk._STAGE_CHUNK + 1)):
+        a = rs.randint(0, 250, size=n).astype(dtype)
+        t = bsk._h2d_staged(a, d)
+        assert t.shape == a.shape and torch.equal(t.cpu(), torch.from_numpy(a))
+        back = bsk._d2h_staged(t)
+        assert back.dtype == a.dtype and np.array_equal(back, a)
+    big = np.zeros(bsk._STAGE_MIN // 4 + 3, np.float32)
+    big[-1] = 7.0
+    assert float(bsk._to_dev(big, d)[-1]) == 7.0 and bsk._to_host(bsk._to_dev(big, d))[-1] == 7.0
+
+
 def test_run_batch_overlapped_on_side_streams_equals_one_batch():
     from superpixel_align_b200 import pipeline
     d = torch.device('cuda', 0)
