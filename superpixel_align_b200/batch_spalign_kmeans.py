@@ -30,6 +30,7 @@ preallocated buffer refilled in place is never mistaken for the previous batch.
 """
 from __future__ import annotations
 
+import threading
 import weakref
 from concurrent.futures import ThreadPoolExecutor
 
@@ -67,6 +68,7 @@ _STAGE_MIN = 96 << 20
 _STAGE_RING = 4
 _STAGE = {}
 _STAGE_POOL = ThreadPoolExecutor(max_workers=_STAGE_RING)
+_STAGE_LOCK = threading.Lock()   # one transfer at a time owns the ring
 
 
 def _stage_ring(dev):
@@ -79,6 +81,11 @@ def _stage_ring(dev):
 
 def _h2d_staged(arr, dev):
     """NumPy (C-contiguous) -> new CUDA tensor of the same shape / dtype."""
+    with _STAGE_LOCK:
+        return _h2d_staged_locked(arr, dev)
+
+
+def _h2d_staged_locked(arr, dev):
     out = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0].reshape(-1)).dtype, device=dev)
     src = arr.reshape(-1).view(np.uint8)
     dst = out.view(-1).view(torch.uint8)
@@ -110,6 +117,11 @@ def _h2d_staged(arr, dev):
 
 def _d2h_staged(t):
     """CUDA tensor (contiguous) -> new NumPy array of the same shape / dtype."""
+    with _STAGE_LOCK:
+        return _d2h_staged_locked(t)
+
+
+def _d2h_staged_locked(t):
     t = t.contiguous()
     dev = t.device
     out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
